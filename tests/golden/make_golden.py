@@ -1,0 +1,237 @@
+"""Generate tests/golden/*.npz / *.json by running the REFERENCE'S OWN methods
+(/root/reference/misinfo_forensics.py, clip_similarity_engine.py) on seeded inputs.
+
+Run in the build container only (`python tests/golden/make_golden.py`); /root/reference
+does not exist on the GPU box, so the fixtures are committed.  The reference ships no
+tests or golden vectors -- these fixtures ARE the parity pin.
+
+Shims (none of them touches hot-path arithmetic):
+  * MisinfoForensics.__init__ needs network weights -> objects are built with
+    object.__new__ and the attributes __init__ would set are assigned by hand;
+  * encoders / tokenisers are the deterministic fakes of tests/fakes.py (they return
+    rows of seeded tables, as plain tensors like transformers-4 did);
+  * cv2 is replaced by tests/fakes.FakeCv2 for analyze_video.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, "/root/reference")
+
+import fakes  # noqa: E402
+import mmf_b200  # noqa: E402,F401
+from mmf_b200 import synth  # noqa: E402
+
+with contextlib.redirect_stdout(io.StringIO()):
+    import misinfo_forensics as ref_mf  # noqa: E402
+    import clip_similarity_engine as ref_ce  # noqa: E402
+
+torch.set_num_threads(1)   # fixed BLAS summation order for the fixtures
+
+
+def make_reference_forensics(image_table, text_table, vault, metadata, detector):
+    f = object.__new__(ref_mf.MisinfoForensics)
+    f.device = torch.device("cpu")
+    f.gemini_available = False
+    f.roberta_tokenizer = fakes.FakeTokenizer()
+    f.detector = detector.eval()
+    f.clip_processor = fakes.FakeClipProcessor()
+    f.clip_model = fakes.FakeClipModel(image_table, text_table).eval()
+    f.vault_embeddings = vault
+    f.vault_metadata = metadata
+    f.vault_loaded = vault is not None
+    f.vault_data = {}
+    f.efficientnet_transform = ref_mf.transforms.Compose([
+        ref_mf.transforms.Resize((224, 224)), ref_mf.transforms.ToTensor(),
+        ref_mf.transforms.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    return f
+
+
+def quiet(fn, *a, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **kw)
+
+
+def gen_cosine():
+    a, b = synth.caption_image_pairs(96, seed=11)
+    # a few adversarial rows: huge / tiny norms, exact duplicates, anti-parallel
+    a[0] *= 1e4
+    b[1] *= 1e-4
+    b[2] = a[2] * 3.0
+    b[3] = -a[3]
+    f = make_reference_forensics(b, a, None, None, fakes.FakeDetector([0.5], [0.5], [0.5]))
+    sims = np.array([f.analyze_consistency(fakes.text_for_id(i), fakes.image_for_id(i))["clip_similarity"]
+                     for i in range(len(a))], dtype=np.float64)
+    eng = object.__new__(ref_ce.CLIPSimilarityEngine)
+    eng.model, eng.processor, eng.threshold, eng.device = f.clip_model, f.clip_processor, 0.25, "cpu"
+    eng.load_image = lambda p: p          # load_image is file IO, outside the hot path
+    es, el = [], []
+    for i in range(len(a)):
+        s, lab = eng.calculate_similarity(fakes.image_for_id(i), fakes.text_for_id(i))
+        es.append(s)
+        el.append(lab == "Match")
+    expl = [eng._generate_explanation(float(s), "Match" if m else "Mismatch") for s, m in zip(es, el)]
+    np.savez_compressed(os.path.join(HERE, "cosine.npz"), text=a, image=b, clip_similarity=sims,
+                        engine_similarity=np.array(es, np.float64), engine_match=np.array(el, bool),
+                        engine_explanation=np.array(expl))
+    print("cosine.npz", sims[:4], int(np.sum(el)), "matches")
+
+
+def _vault_case(f, q_ids, caption_ids, k):
+    idx = np.full((len(q_ids), k), -1, np.int64)
+    sim = np.full((len(q_ids), k), np.nan, np.float64)
+    disc = np.zeros(len(q_ids), np.float64)
+    tsim = np.zeros(len(q_ids), np.float64)
+    nmatch = np.zeros(len(q_ids), np.int64)
+    for r, (qi, ci) in enumerate(zip(q_ids, caption_ids)):
+        cap = fakes.text_for_id(ci) if ci >= 0 else None
+        out = f.search_vault(fakes.image_for_id(qi), user_caption=cap, top_k=k)
+        assert out["vault_available"] is True
+        nmatch[r] = len(out["matches"])
+        for j, m in enumerate(out["matches"]):
+            idx[r, j] = fakes.id_of_text(m["title"])
+            sim[r, j] = m["similarity"]
+        disc[r] = out["vault_discrepancy"]
+        tsim[r] = out["text_similarity"]
+    return idx, sim, disc, tsim, nmatch
+
+
+def gen_vault():
+    n, nq = 3000, 64
+    g = np.random.default_rng(77)
+    vault = synth.vault_rows(n, seed=91) * g.uniform(0.2, 9.0, size=(n, 1)).astype(np.float32)
+    q, planted_row, planted_cos = synth.queries(nq, n, seed=92, plant_frac=0.5, vault_seed=91)
+    q[0] = vault[17] * 0.37                      # exact duplicate direction -> cos 1
+    q[1] = vault[2999]
+    # text tower table: captions 0..nq-1, titles are "caption #<row>" -> reuse one table of n rows
+    text_table = np.random.default_rng(93).standard_normal((n, 512)).astype(np.float32)
+    for i in range(0, nq, 3):                    # make some captions close to their match's title
+        if planted_row[i] >= 0:
+            text_table[i] = synth.planted_query(text_table[planted_row[i]], 0.7, g)
+    meta = [{"title": fakes.text_for_id(i), "url": f"http://x/{i}", "date": f"2020-01-{i % 28 + 1:02d}"}
+            for i in range(n)]
+    det = fakes.FakeDetector([0.5], [0.5], [0.5])
+    out = dict(vault=vault, queries=q, text_table=text_table[:nq].copy(), planted_row=planted_row,
+               planted_cos=planted_cos)
+    f = make_reference_forensics(q, text_table, vault, meta, det)
+    ids = np.arange(nq)
+    for k in (5, 10):
+        idx, sim, disc, tsim, nm = _vault_case(f, ids, ids, k)
+        out.update({f"idx_k{k}": idx, f"sim_k{k}": sim, f"disc_k{k}": disc, f"tsim_k{k}": tsim})
+    # titles needed to reproduce text_similarity: row of the top match per query
+    out["title_rows_needed"] = out["idx_k5"][:, 0]
+    out["title_table"] = text_table[out["idx_k5"][:, 0]]
+    # fp16 vault (what a CUDA-built pickle holds, train_clip_detective.py:550): reference keeps fp16
+    f16 = make_reference_forensics(q, text_table, vault.astype(np.float16), meta, det)
+    idx, sim, disc, _, _ = _vault_case(f16, ids, -np.ones(nq, np.int64), 5)
+    out.update(idx_f16_k5=idx, sim_f16_k5=sim, disc_f16_k5=disc)
+    # k > N and tiny vault
+    small = vault[:3].copy()
+    fs = make_reference_forensics(q, text_table, small, meta[:3], det)
+    idx, sim, disc, _, nm = _vault_case(fs, ids[:8], -np.ones(8, np.int64), 5)
+    out.update(small_idx=idx, small_sim=sim, small_disc=disc, small_nmatch=nm)
+    # zero-norm vault row -> NaN similarity ranks FIRST and kills the discrepancy
+    zv = vault[:50].copy()
+    zv[7] = 0.0
+    fz = make_reference_forensics(q, text_table, zv, meta[:50], det)
+    with np.errstate(all="ignore"):
+        idx, sim, disc, _, _ = _vault_case(fz, ids[:4], -np.ones(4, np.int64), 5)
+    out.update(nan_idx=idx, nan_sim=sim, nan_disc=disc)
+    # vault not loaded
+    fn = make_reference_forensics(q, text_table, None, None, det)
+    out["not_loaded"] = np.array(json.dumps(fn.search_vault(fakes.image_for_id(0), "caption #0")))
+    np.savez_compressed(os.path.join(HERE, "vault.npz"), **out)
+    print("vault.npz disc>0:", int((out["disc_k5"] > 0).sum()), "tsim>0:", int((out["tsim_k5"] != 0).sum()))
+
+
+def gen_fusion():
+    n = 512
+    sd = synth.fusion_state_dict(0)
+    det = fakes.FakeDetector([0.5], [0.5], [0.5])
+    det.fusion_layer.load_state_dict(sd)
+    g = np.random.default_rng(42)
+    x = np.concatenate([g.uniform(0, 1, (n, 3)), g.uniform(-0.2, 1.0, (n, 1)),
+                        np.where(g.uniform(size=(n, 1)) < 0.3, g.uniform(0.85, 1.0, (n, 1)), 0.0)],
+                       axis=1).astype(np.float32)
+    x[0] = 0.0
+    x[1] = [1, 1, 1, 1, 1]
+    x[2] = [50.0, -30.0, 7.0, -1.0, 0.99]       # out-of-range inputs still go through the MLP
+    f = make_reference_forensics(np.zeros((1, 512), np.float32), np.zeros((1, 512), np.float32), None, None, det)
+    outs = [f.fusion_verdict(dict(zip(("ai_score", "misinfo_score", "deepfake_score", "clip_similarity",
+                                       "vault_discrepancy"), map(float, row)))) for row in x]
+    # a "trained" set of weights with larger magnitude, so probabilities span (0,1)
+    det2 = fakes.FakeDetector([0.5], [0.5], [0.5], fusion_seed=5)
+    f2 = make_reference_forensics(np.zeros((1, 512), np.float32), np.zeros((1, 512), np.float32), None, None, det2)
+    outs2 = [f2.fusion_verdict(dict(zip(("ai_score", "misinfo_score", "deepfake_score", "clip_similarity",
+                                        "vault_discrepancy"), map(float, row)))) for row in x]
+    sv = {("w_" + k): v.numpy() for k, v in sd.items()}
+    sv.update({("w2_" + k): v.detach().numpy() for k, v in det2.fusion_layer.state_dict().items()})
+    for tag, o in (("", outs), ("2", outs2)):
+        sv["real" + tag] = np.array([r["real_probability"] for r in o], np.float64)
+        sv["fake" + tag] = np.array([r["fake_probability"] for r in o], np.float64)
+        sv["verdict" + tag] = np.array([r["verdict"] for r in o], np.int64)
+        sv["confidence" + tag] = np.array([r["confidence"] for r in o], np.float64)
+    np.savez_compressed(os.path.join(HERE, "fusion.npz"), x=x, **sv)
+    print("fusion.npz fake-rate", sv["verdict"].mean(), sv["verdict2"].mean())
+
+
+def gen_analyze():
+    """Full MisinfoForensics.analyze / analyze_video on planted producers."""
+    n, ns = 400, 24
+    g = np.random.default_rng(5)
+    vault = synth.vault_rows(n, seed=191)
+    img, planted_row, planted_cos = synth.queries(ns, n, seed=192, plant_frac=0.6, vault_seed=191)
+    txt = np.random.default_rng(193).standard_normal((n, 512)).astype(np.float32)
+    for i in range(ns):                       # caption i correlated with image i at a random level
+        txt[i] = synth.planted_query(img[i], float(g.uniform(-0.1, 0.6)), g) * 4.0
+    ai, mis, deep = (g.uniform(0.02, 0.98, ns) for _ in range(3))
+    meta = [{"title": fakes.text_for_id(i), "url": f"http://x/{i}"} if i % 2 else
+            {"title": fakes.text_for_id(i), "url": f"http://x/{i}", "date": "2021-05-05"} for i in range(n)]
+    det = fakes.FakeDetector(ai, mis, deep, fusion_seed=5)
+    f = make_reference_forensics(img, txt, vault, meta, det)
+    cases = []
+    for i in range(ns):
+        mode = ("both", "text", "image")[i % 3] if i >= 6 else "both"
+        text = fakes.text_for_id(i) if mode in ("both", "text") else None
+        image = fakes.image_for_id(i) if mode in ("both", "image") else None
+        res = quiet(f.analyze, text=text, image_path=image, verbose=(i % 2 == 0))
+        cases.append({"id": i, "mode": mode, "result": res})
+    # video: frames are image ids; with and without text
+    sys.modules["cv2"] = fakes.FakeCv2
+    vids = []
+    for path, text in (("fake://fps=2;ids=0,1,2,3,4,5,6,7,8,9,10,11,12,13", fakes.text_for_id(3)),
+                       ("fake://fps=1;ids=20,21,22,23", None),
+                       ("fake://fps=0;ids=5,6", fakes.text_for_id(5))):
+        v = quiet(f.analyze_video, path, text=text, max_frames=12, stride_seconds=1.0)
+        v.pop("best_frame")
+        res = quiet(f.analyze, text=text, video_path=path, verbose=False)
+        vids.append({"path": path, "text": text, "video": v, "result": res})
+    np.savez_compressed(os.path.join(HERE, "analyze_inputs.npz"), vault=vault, image_table=img, text_table=txt,
+                        ai=ai, misinfo=mis, deepfake=deep, planted_row=planted_row, planted_cos=planted_cos)
+    with open(os.path.join(HERE, "analyze_cases.json"), "w") as fh:
+        json.dump({"metadata": meta, "cases": cases, "videos": vids,
+                   "versions": {"torch": torch.__version__, "numpy": np.__version__}}, fh, indent=1)
+    nf = sum(c["result"]["verdict"] for c in cases)
+    print("analyze_cases.json", len(cases), "cases,", nf, "FAKE;", len(vids), "videos")
+
+
+if __name__ == "__main__":
+    gen_cosine()
+    gen_vault()
+    gen_fusion()
+    gen_analyze()
+    with open(os.path.join(HERE, "MANIFEST.json"), "w") as fh:
+        json.dump({"generator": "tests/golden/make_golden.py", "reference": "/root/reference (unmodified)",
+                   "torch": torch.__version__, "numpy": np.__version__, "threads": 1,
+                   "python": sys.version.split()[0]}, fh, indent=1)
