@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""Benchmark of the scoring hot path (BASELINE.json metric: vault queries/s + roofline).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl reference]
+
+A step is one pass of the hot path over one batch of synthetic embeddings:
+caption/image cosine -> Truth-Vault top-k + discrepancy -> fusion judge.
+
+Workloads (BASELINE.json configs):
+  c2 (default)  256 queries vs a 1M x 512 fp32-exact vault, top-10, + cosine + fusion (configs[1]).
+                N > 1: every rank is an independent replica with its own 256-query batch
+                (queries shard with no collective) -> "scaling": "weak".
+  c3            batch-1 latency mode: 1 query vs the 1M fp32-exact vault, top-10 (configs[2]).
+  c4            4096 queries vs a 10M x 512 bf16 vault ROW-SHARDED over the N ranks, top-100,
+                one NCCL all-gather of the per-shard candidates + merge (configs[3]) -> "strong".
+`--impl reference` times the reference's own CPU algorithm (the oracle port of
+misinfo_forensics.py:438-464: per-query renormalisation of the whole vault in NumPy) on the
+host cores, rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(q=256, rows=1_000_000, k=10, mode="fp32", desc="256 queries vs 1M-row fp32-exact vault, top-10 + caption/image cosine + fusion judge"),
+    "c3": dict(q=1, rows=1_000_000, k=10, mode="fp32", desc="batch-1 latency: 1 query vs 1M-row fp32-exact vault, top-10"),
+    "c4": dict(q=4096, rows=10_000_000, k=100, mode="bf16", desc="4096 queries vs 10M-row bf16 vault row-sharded over the ranks, top-100, all-gather merge"),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------- CPU side (oracle)
+def cpu_reference_step(vault_host, q_host, text_host, img_host, head, fusion_w, n_sample, k):
+    """The reference's own algorithm on `n_sample` samples of the batch: cosine (:399-404),
+    as-shipped vault search (:438-464, whole-vault renormalisation per query) and fusion_verdict."""
+    import oracle
+    for i in range(n_sample):
+        sim = oracle.cosine_pairs(text_host[i:i + 1], img_host[i:i + 1], scalar_loop=True)[0]
+        _, _, disc = oracle.vault_search_as_shipped(vault_host, q_host[i], k)
+        oracle.fusion_verdict(fusion_w, {"ai_score": head[i, 0], "misinfo_score": head[i, 1], "deepfake_score": head[i, 2],
+                                         "clip_similarity": float(sim), "vault_discrepancy": disc})
+
+
+def cpu_batched_step(vault_norm_t, q_host, k):
+    """The 'batched torch restatement' of BASELINE.md 4(2): normalise once, Qn @ Vn.T, torch.topk."""
+    q = torch.from_numpy(q_host)
+    qn = q / q.norm(dim=-1, keepdim=True)
+    s = qn @ vault_norm_t.T
+    return torch.topk(s, k, dim=1)
+
+
+def run_reference_arm(args, wl):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from mmf_b200 import synth
+    import oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    rows, k = wl["rows"], wl["k"]
+    g = np.random.default_rng(synth.VAULT_SEED)
+    vault = g.standard_normal((rows, 512), dtype=np.float32)
+    if wl["mode"] == "bf16":
+        vault = torch.from_numpy(vault).bfloat16().float().numpy()
+    n_sample = 1
+    q = np.random.default_rng(synth.QUERY_SEED).standard_normal((max(n_sample, 1), 512), dtype=np.float32)
+    a, b = synth.caption_image_pairs(max(n_sample, 8))
+    head = synth.head_scores(max(n_sample, 8))
+    fw = synth.fusion_state_dict()
+    for _ in range(args.warmup):
+        cpu_reference_step(vault, q, a, b, head, fw, n_sample, k)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(vault, q, a, b, head, fw, n_sample, k)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = n_sample / dt
+    cores = os.cpu_count() or 1
+    sample = f"{n_sample} query per step vs the full {rows}-row vault, as-shipped per-query renormalisation (NumPy)"
+    print(json.dumps({
+        "impl": "reference", "metric": "vault queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "vault_rows": rows, "dim": 512, "top_k": k},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ----------------------------------------------------------------------------- GPU side
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="mmf_b200", choices=["mmf_b200", "reference"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "stream", "mma"])
+    ap.add_argument("--rows", type=int, default=0, help="override vault rows (debug only; the line then says so)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.rows:
+        wl["rows"] = args.rows
+        wl["desc"] += f" [rows overridden to {args.rows}]"
+    if args.impl == "reference":
+        return run_reference_arm(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    rank, local_rank, world = dist_env()
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import mmf_b200
+    from mmf_b200 import synth
+    hbm_peak, tf_peak, tf_sustained, peak_kind = peaks()
+    eng = mmf_b200.Engine(dev)
+    Q, K, total_rows, mode = wl["q"], wl["k"], wl["rows"], wl["mode"]
+    sharded = args.workload == "c4" and world > 1
+    plan = mmf_b200.ShardPlan(total_rows, world if sharded else 1)
+    lo, hi = plan.bounds(rank if sharded else 0)
+    n_local = hi - lo
+
+    # synthetic vault shard generated on the device in 1M-row slabs (seeded by the global slab id,
+    # so a shard never depends on the others); un-normalised on purpose: vault_load normalises
+    slab = 1_000_000
+    parts = []
+    for s0 in range(lo - lo % slab, hi, slab):
+        g = torch.Generator(device=dev).manual_seed(synth.VAULT_SEED + s0 // slab)
+        blk = torch.randn(min(slab, total_rows - s0), 512, device=dev, generator=g)
+        parts.append(blk[max(lo, s0) - s0:min(hi, s0 + slab) - s0])
+    vault_rows = torch.cat(parts) if len(parts) > 1 else parts[0]
+    del parts
+    vault = mmf_b200.TruthVault(eng, vault_rows, None, mode=mode, rank=rank if sharded else 0, world=world if sharded else 1,
+                                n_total=total_rows, row_offset=lo)
+    eng.fusion_load(synth.fusion_state_dict())
+
+    # per-step inputs in PINNED host memory (e2e) and resident in HBM (device-timed `value`).
+    # c2 replicas get a different query batch per rank; the sharded c4 batch is the same on all ranks.
+    seed = synth.QUERY_SEED + (0 if sharded else rank)
+    gq = np.random.default_rng(seed)
+    q_host = torch.from_numpy(gq.standard_normal((Q, 512), dtype=np.float32) * 3.0)
+    n_plant = max(1, Q // 10)
+    pick = torch.from_numpy(gq.integers(0, n_local, n_plant))
+    planted = vault_rows[pick.to(dev)].cpu()
+    noise = torch.from_numpy(gq.standard_normal((n_plant, 512), dtype=np.float32))
+    cosv = torch.tensor([synth.PLANT_COSINES[i % 5] for i in range(n_plant)])
+    pn = planted / planted.norm(dim=1, keepdim=True)
+    noise = noise - (noise * pn).sum(1, keepdim=True) * pn
+    noise = noise / noise.norm(dim=1, keepdim=True)
+    q_host[:n_plant] = (cosv[:, None] * pn + torch.sqrt(1 - cosv ** 2)[:, None] * noise) * 2.0
+    if sharded:                         # one batch for all ranks: rank 0's (its planted rows live in shard 0)
+        qd = q_host.to(dev)
+        dist.broadcast(qd, 0)
+        pd = pick.to(dev)
+        dist.broadcast(pd, 0)
+        q_host, pick = qd.cpu(), pd.cpu()
+    a_np, b_np = synth.caption_image_pairs(Q, seed=seed + 1)
+    text_host = torch.from_numpy(a_np).pin_memory()
+    img_host = q_host.pin_memory()          # the image embedding is both the cosine operand and the vault query
+    head_host = torch.from_numpy(synth.head_scores(Q, seed=seed + 2)).pin_memory()
+    text_dev, img_dev, head_dev = text_host.to(dev), img_host.to(dev), head_host.to(dev)
+    keep_vault_rows = vault_rows if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    del vault_rows
+
+    def step_device():
+        return mmf_b200.score_batch(eng, vault, text_dev, img_dev, head_dev, None, K, args.algo)
+
+    def step_e2e():
+        out = mmf_b200.score_batch(eng, vault, text_host, img_host, head_host, None, K, args.algo)
+        return (out["verdict"].cpu(), out["probs"].cpu(), out["vault_scores"].cpu(), out["vault_rows"].cpu(),
+                out["clip_similarity"].cpu(), out["vault_discrepancy"].cpu())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # sanity of the timed path before timing it (planted rows must be found at their cosine)
+    out = step_device()
+    torch.cuda.synchronize()
+    got_rows = out["vault_rows"][:n_plant, 0].cpu()
+    assert torch.equal(got_rows, pick + (0 if sharded else lo)), "planted rows not recovered"
+    tol = 1e-2 if mode == "bf16" else 1e-5
+    assert torch.allclose(out["vault_scores"][:n_plant, 0].cpu(), cosv, atol=tol), "planted cosines off"
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    search_ev = []
+    ev[0].record()
+    for _ in range(args.steps):
+        # inner events bracket the vault search alone (dominant kernel) on the launching stream
+        sim = eng.cosine_pairs(text_dev, img_dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        vs, vr, disc = vault.search(img_dev, K, mmf_b200.VAULT_THRESHOLD, args.algo)
+        e1.record()
+        search_ev.append((e0, e1))
+        x = torch.cat([head_dev, sim[:, None], disc[:, None]], dim=1)
+        eng.fusion_forward(x)
+    ev[1].record()
+    barrier()
+    launches = eng.launch_count - launches0
+    step_ms = ev[0].elapsed_time(ev[1]) / args.steps
+    search_ms = statistics.mean(a.elapsed_time(b) for a, b in search_ev)
+    clocks = sampler.stop() if sampler else None
+
+    # e2e: same work through the public API with HOST buffers, copies inside the timed region
+    for _ in range(max(2, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step_e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    h2d = text_host.numel() * 4 + img_host.numel() * 4 + head_host.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in res)
+
+    if world > 1:
+        t = torch.tensor([step_ms, search_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, search_ms, e2e_ms = t.tolist()
+    queries_per_step = Q if sharded else Q * world
+    value = queries_per_step / (step_ms * 1e-3)
+    e2e_value = queries_per_step / (e2e_ms * 1e-3)
+
+    elem = 2 if mode == "bf16" else 4
+    if args.workload == "c4":
+        flops = 2.0 * Q * n_local * 512
+        achieved = flops / (search_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                "traffic": None, "kernel": "vault search (query prep + search + top-k select), per rank",
+                "algorithmic_flops_per_launch": flops, "frac_of_sustained_peak": achieved / tf_sustained}
+    else:
+        nbytes = float(n_local) * 512 * elem
+        achieved = nbytes / (search_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": "vault search (query prep + search + top-k select)",
+                "algorithmic_bytes_per_launch": nbytes,
+                "tensor_tflops_algorithmic": 2.0 * Q * n_local * 512 / (search_ms * 1e-3) / 1e12}
+    roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind})"
+    roof["kernel_ms"] = search_ms
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        vault_host = keep_vault_rows.cpu().numpy()
+        if mode == "bf16":
+            vault_host = torch.from_numpy(vault_host).bfloat16().float().numpy()
+        fw = synth.fusion_state_dict()
+        qh, th, hh = q_host.numpy(), text_host.numpy(), head_host.numpy()
+        n_sample, t_budget = 0, 12.0
+        t0 = time.perf_counter()
+        while True:
+            cpu_reference_step(vault_host, qh[n_sample:n_sample + 1], th[n_sample:n_sample + 1], qh[n_sample:n_sample + 1],
+                               hh[n_sample:n_sample + 1], fw, 1, K)
+            n_sample += 1
+            if time.perf_counter() - t0 > t_budget or n_sample >= Q:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_sample / dt, "unit": "queries/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"{n_sample} of the {Q} queries of one step, each vs the full {n_local}-row vault, reference "
+                         "algorithm as shipped (NumPy, whole-vault renormalisation per query)"}
+        # the batched restatement, for context; bounded sample of the vault rows
+        sub = min(n_local, 200_000)
+        vn = torch.from_numpy(oracle.vault_normalise(vault_host[:sub]).astype(np.float32))
+        cpu_batched_step(vn, qh, min(K, sub))
+        t0 = time.perf_counter()
+        cpu_batched_step(vn, qh, min(K, sub))
+        dtb = (time.perf_counter() - t0) * (n_local / sub)
+        cpu["batched_restatement"] = {"value": Q / dtb, "unit": "queries/s", "threads": torch.get_num_threads(),
+                                      "sample": f"all {Q} queries vs {sub} vault rows, time scaled to {n_local} rows; "
+                                                "normalise once + Qn@Vn.T + torch.topk"}
+        del vault_host, vn
+
+    if rank == 0:
+        line = {
+            "metric": "vault queries/s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "c4" else "weak", "vs_baseline": None,
+            "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "queries_per_step": queries_per_step, "vault_rows_total": total_rows,
+                       "vault_rows_per_gpu": n_local, "dim": 512, "top_k": K, "vault_mode": mode, "algo": args.algo,
+                       "parallelism": ("vault row-sharded x%d + NCCL all-gather merge" % world) if sharded else
+                                      ("replica x%d, queries sharded, no collective" % world),
+                       "l2": f"vault shard {n_local * 512 * elem / 1e6:.0f} MB streamed per step (> 126 MB L2), no flush needed"},
+            "roofline": roof, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "api": "mmf_b200.score_batch on pinned host tensors + .cpu() of the results"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libmmf_b200.so (sm_100a only) in-tree.  Usage: ./build.sh [extra nvcc flags]
+set -euo pipefail
+cd "$(dirname "$0")"
+PKG="multi-modal-misinformation-detection-with-explanation-generation_b200"
+SRC="$PKG/csrc"
+OUT="$PKG/libmmf_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall "$@")
+mkdir -p build
+pids=()
+for f in api cosine fusion vault_build vault_stream vault_mma; do
+  if [ ! -f "build/$f.o" ] || [ "$SRC/$f.cu" -nt "build/$f.o" ] || [ -n "$(find "$SRC" include -name '*.cuh' -newer "build/$f.o" -o -name '*.h' -newer "build/$f.o")" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$SRC/$f.cu" -o "build/$f.o" &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+"$NVCC" -shared -o "$OUT" build/api.o build/cosine.o build/fusion.o build/vault_build.o build/vault_stream.o build/vault_mma.o
+echo "built $OUT"

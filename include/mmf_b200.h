@@ -1,0 +1,150 @@
+/* libmmf_b200.so -- C ABI of the B200-native scoring hot path.
+ *
+ * The reference (yashingle-ai/Multi-Modal-Misinformation-Detection-with-Explanation-
+ * Generation) has NO plugin / FFI boundary: the hot path is inline torch / NumPy
+ * arithmetic inside Python methods.  Each entry point below therefore names the inline
+ * reference lines it replaces (paths relative to the reference checkout); the binding a
+ * maintainer adds on the reference side is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no C++ types or exceptions cross the boundary; every call returns an int
+ *    status (MMF_OK == 0, negatives are errors) and mmf_last_error() has the detail;
+ *  - unless a name ends in _host, data pointers are DEVICE pointers on the handle's
+ *    device (torch.Tensor.data_ptr() passes zero-copy) and the call is ASYNCHRONOUS on
+ *    the cudaStream_t given as `stream` (torch.cuda.current_stream().cuda_stream); no
+ *    hidden synchronisation.  *_host calls take host pointers, include the H2D / D2H
+ *    copies and return after the result is in host memory;
+ *  - a handle is not thread-safe: one handle per (process, device), calls serialised by
+ *    the caller (the reference is single-threaded and synchronous);
+ *  - there is no CPU fallback: without a CUDA device mmf_create fails with
+ *    MMF_ERR_NO_DEVICE.
+ */
+#ifndef MMF_B200_H
+#define MMF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mmf_handle mmf_handle;
+typedef void* mmf_stream_t; /* cudaStream_t */
+
+enum mmf_status {
+  MMF_OK = 0,
+  MMF_ERR_BAD_ARG = -1,
+  MMF_ERR_CUDA = -2,
+  MMF_ERR_NOT_LOADED = -3, /* vault / fusion weights not loaded (reference: vault_loaded == False) */
+  MMF_ERR_NO_DEVICE = -4,
+  MMF_ERR_UNSUPPORTED = -5,
+  MMF_ERR_NOMEM = -6
+};
+
+enum mmf_dtype { MMF_F32 = 0, MMF_F16 = 1, MMF_BF16 = 2, MMF_F64 = 3 };
+
+/* How the vault shard is kept in HBM.
+ *  MMF_VAULT_FP32: fp32-exact.  Rows are L2-normalised in fp32 and stored as two fp16
+ *                  planes hi/lo (v*2^8 = hi + lo, 22+ significant bits, 4 B/element --
+ *                  the same bytes as fp32) so that the SAME resident copy feeds both the
+ *                  HBM-streaming kernel (reconstructs hi+lo in fp32) and the tcgen05
+ *                  kernel (3 f16 MMA passes, fp32 accumulate).  Tolerance 1e-5.
+ *  MMF_VAULT_BF16: rows normalised in fp32, rounded to bf16 (2 B/element). Tolerance 1e-2. */
+enum mmf_vault_mode { MMF_VAULT_FP32 = 0, MMF_VAULT_BF16 = 1 };
+
+/* Which search kernel mmf_vault_search uses. AUTO: streaming kernel for small query
+ * batches (HBM-bound), tcgen05 kernel for large ones (tensor-bound). */
+enum mmf_search_algo { MMF_ALGO_AUTO = 0, MMF_ALGO_STREAM = 1, MMF_ALGO_MMA = 2 };
+
+#define MMF_MAX_TOP_K 256
+#define MMF_FUSION_PARAMS 2530 /* 64*5+64 + 32*64+32 + 2*32+2, misinfo_forensics.py:83-90 */
+
+const char* mmf_version(void);
+int mmf_arch(void); /* 100: built for sm_100a only */
+const char* mmf_status_string(int status);
+
+/* One handle per (process, device).  Owns the uploaded vault shard, the packed fusion
+ * weights and scratch; nothing else. */
+int mmf_create(int device_ordinal, mmf_handle** out);
+int mmf_destroy(mmf_handle* h);
+const char* mmf_last_error(const mmf_handle* h);
+
+/* ---- CLIP caption<->image consistency ------------------------------------------------
+ * Replaces misinfo_forensics.py:399-404 (analyze_consistency: normalise both embeddings,
+ * dot) and clip_similarity_engine.py:103-111 (same cosine + `sim >= threshold` label);
+ * also misinfo_forensics.py:481-484 (caption<->headline text similarity).
+ * a, b: (n_pairs, dim) fp32 row-major; out_sim: (n_pairs) fp32;
+ * out_match: (n_pairs) uint8, 1 where (double)sim >= match_threshold; may be NULL. */
+int mmf_cosine_pairs(mmf_handle* h, const float* a, const float* b, int64_t n_pairs, int dim,
+                     double match_threshold, float* out_sim, uint8_t* out_match, mmf_stream_t stream);
+
+/* ---- Truth Vault ---------------------------------------------------------------------
+ * mmf_vault_load replaces the per-query renormalisation of misinfo_forensics.py:443-445
+ * (Vn = V / ||V||, hoisted: done once at load) and uploads this rank's row shard.
+ * rows: (n_rows, dim) row-major of src_dtype, host pointer (rows_on_device == 0) or device
+ * pointer.  row_offset: global id of the shard's first row (row-sharding).
+ * dim must be 512 (CLIP ViT-B/32 projection, misinfo_forensics.py:78-79). Synchronous. */
+int mmf_vault_load(mmf_handle* h, const void* rows, int rows_on_device, int64_t n_rows, int dim,
+                   int src_dtype, int vault_mode, int64_t row_offset);
+int mmf_vault_unload(mmf_handle* h);
+int mmf_vault_info(const mmf_handle* h, int64_t* n_rows, int* dim, int* vault_mode, int64_t* row_offset);
+
+/* Replaces misinfo_forensics.py:438-440 (query normalise), :446 (similarities), :449-450
+ * (argsort top-k, descending; ties: higher row id first; NaN ranks first like np.argsort)
+ * and :463-464 (discrepancy = top if (double)top > threshold else 0).
+ * queries: (n_queries, dim) fp32, un-normalised embeddings.
+ * out_scores (n_queries, top_k) fp32, out_rows (n_queries, top_k) int64 GLOBAL row ids;
+ * if top_k > n_rows the tail is filled with NaN / -1 (the reference returns n_rows items).
+ * out_discrepancy (n_queries) fp32, may be NULL. */
+int mmf_vault_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                     int algo, float* out_scores, int64_t* out_rows, float* out_discrepancy,
+                     mmf_stream_t stream);
+
+/* Same, host buffers: H2D of the queries, search, D2H of the results, stream sync. */
+int mmf_vault_search_host(mmf_handle* h, const float* queries_host, int64_t n_queries, int top_k,
+                          double threshold, int algo, float* out_scores_host, int64_t* out_rows_host,
+                          float* out_discrepancy_host);
+
+/* Row-sharded search: this rank's local top-k as packed candidates, one
+ * uint64 per candidate = (order-preserving score key << 32) | global row id; 0 = empty.
+ * out_packed: (n_queries, top_k) uint64.  The caller all-gathers the buffers of all
+ * ranks (NCCL) and calls mmf_topk_merge. */
+int mmf_vault_search_candidates(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int algo,
+                                uint64_t* out_packed, mmf_stream_t stream);
+
+/* packed: (n_lists, n_queries, k_in) uint64 candidates (e.g. the all-gathered shards).
+ * Selects the global top_k per query under the same total order, so the result is
+ * independent of the sharding.  Outputs as mmf_vault_search. */
+int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n_queries, int k_in, int top_k,
+                   double threshold, float* out_scores, int64_t* out_rows, float* out_discrepancy,
+                   mmf_stream_t stream);
+
+/* ---- Fusion judge --------------------------------------------------------------------
+ * Weights of MultiModalMisinfoDetector.fusion_layer (misinfo_forensics.py:83-90), in the
+ * order and nn.Linear layout of the .pth (train_fusion_judge.py:259-267):
+ * [0.weight (64,5) | 0.bias (64) | 3.weight (32,64) | 3.bias (32) | 5.weight (2,32) | 5.bias (2)]
+ * = MMF_FUSION_PARAMS fp32, HOST pointer.  Call again after the trainer mutates them. */
+int mmf_fusion_load(mmf_handle* h, const float* params_host);
+
+/* Replaces misinfo_forensics.py:587-608: x (n,5) fp32 = [ai, misinfo, deepfake,
+ * clip_similarity, vault_discrepancy] -> probs (n,2) fp32 [real, fake] (softmax),
+ * verdict (n) int32 = fake > 0.5, confidence (n) fp32.  out_verdict/out_confidence may be NULL. */
+int mmf_fusion_forward(mmf_handle* h, const float* x, int64_t n, float* out_probs, int32_t* out_verdict,
+                       float* out_confidence, mmf_stream_t stream);
+
+/* Batched MisinfoForensics.analyze downstream of the encoders (misinfo_forensics.py:
+ * 866-900): per row, modality bit0 = has text, bit1 = has image/video.
+ *   both  -> fusion judge on [ai, misinfo, deepfake, clip_sim, vault_disc]
+ *   text  -> fake = misinfo;  visual -> fake = max(deepfake, vault_disc);  none -> 0.5
+ * (fallbacks clamped to [0,1], real = 1 - fake).  scores: (n,5) fp32 as above.
+ * Outputs as mmf_fusion_forward. */
+int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modality, int64_t n, float* out_probs,
+                      int32_t* out_verdict, float* out_confidence, mmf_stream_t stream);
+
+/* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
+int64_t mmf_launch_count(const mmf_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMF_B200_H */

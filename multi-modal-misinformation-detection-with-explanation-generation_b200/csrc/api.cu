@@ -1,0 +1,210 @@
+// C-ABI glue: handle lifetime, error strings, scratch, search dispatch, host-buffer entry.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+#include <new>
+
+int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                      float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st);
+int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                   float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st);
+int mmf_mma_supported(const mmf_handle* h, int64_t n_queries, int top_k);
+void mmf_mma_destroy(mmf_handle* h);
+int mmf_fill_empty(mmf_handle* h, int64_t n_queries, int top_k, float* out_scores, int64_t* out_rows,
+                   uint64_t* out_packed, float* out_disc, cudaStream_t st);
+
+int mmf_set_error(mmf_handle* h, int status, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    h->last_error = buf;
+  }
+  return status;
+}
+
+int mmf_ensure_scratch(mmf_handle* h, size_t bytes, cudaStream_t stream) {
+  if (bytes <= h->scratch_bytes) return MMF_OK;
+  // growth is rare (first call / larger batch): drain the device, then reallocate
+  MMF_CUDA_OK(h, cudaDeviceSynchronize());
+  if (h->scratch) MMF_CUDA_OK(h, cudaFree(h->scratch));
+  h->scratch = nullptr;
+  h->scratch_bytes = 0;
+  const size_t want = std::max(bytes + bytes / 4, (size_t)1 << 22);
+  if (cudaMalloc(&h->scratch, want) != cudaSuccess) {
+    cudaGetLastError();
+    return mmf_set_error(h, MMF_ERR_NOMEM, "cannot allocate %zu bytes of scratch", want);
+  }
+  h->scratch_bytes = want;
+  MMF_CUDA_OK(h, cudaMemsetAsync(h->scratch, 0, 65536, stream));   // arrival counters start at 0
+  return MMF_OK;
+}
+
+static int ensure_pinned(mmf_handle* h, size_t bytes) {
+  if (bytes <= h->pinned_bytes) return MMF_OK;
+  if (h->pinned) MMF_CUDA_OK(h, cudaFreeHost(h->pinned));
+  h->pinned = nullptr;
+  h->pinned_bytes = 0;
+  const size_t want = std::max(bytes, (size_t)1 << 20);
+  MMF_CUDA_OK(h, cudaMallocHost(&h->pinned, want));
+  h->pinned_bytes = want;
+  return MMF_OK;
+}
+
+extern "C" const char* mmf_version(void) { return "mmf_b200 0.1.0 (sm_100a)"; }
+extern "C" int mmf_arch(void) { return 100; }
+
+extern "C" const char* mmf_status_string(int status) {
+  switch (status) {
+    case MMF_OK: return "ok";
+    case MMF_ERR_BAD_ARG: return "bad argument";
+    case MMF_ERR_CUDA: return "CUDA error";
+    case MMF_ERR_NOT_LOADED: return "not loaded";
+    case MMF_ERR_NO_DEVICE: return "no CUDA device";
+    case MMF_ERR_UNSUPPORTED: return "unsupported";
+    case MMF_ERR_NOMEM: return "out of device memory";
+  }
+  return "unknown status";
+}
+
+extern "C" int mmf_create(int device_ordinal, mmf_handle** out) {
+  if (!out) return MMF_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return MMF_ERR_NO_DEVICE; }
+  if (device_ordinal < 0 || device_ordinal >= n) return MMF_ERR_BAD_ARG;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device_ordinal) != cudaSuccess) return MMF_ERR_CUDA;
+  if (prop.major != 10) return MMF_ERR_UNSUPPORTED;      // sm_100a code only; no other path exists
+  mmf_handle* h = new (std::nothrow) mmf_handle();
+  if (!h) return MMF_ERR_NOMEM;
+  h->device = device_ordinal;
+  h->sm_count = prop.multiProcessorCount;
+  if (cudaSetDevice(device_ordinal) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return MMF_ERR_CUDA;
+  }
+  *out = h;
+  return MMF_OK;
+}
+
+extern "C" int mmf_destroy(mmf_handle* h) {
+  if (!h) return MMF_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  mmf_mma_destroy(h);
+  if (h->vault) cudaFree(h->vault);
+  if (h->fusion_params) cudaFree(h->fusion_params);
+  if (h->scratch) cudaFree(h->scratch);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->io) cudaFree(h->io);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+  return MMF_OK;
+}
+
+extern "C" const char* mmf_last_error(const mmf_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+extern "C" int64_t mmf_launch_count(const mmf_handle* h) { return h ? h->launches : 0; }
+
+static int search_dispatch(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                           int algo, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
+                           cudaStream_t st, const char* who) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n_queries < 0 || top_k <= 0 || (n_queries > 0 && !queries))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "%s: bad argument (n_queries=%lld top_k=%d)", who, (long long)n_queries, top_k);
+  if (top_k > MMF_MAX_TOP_K)
+    return mmf_set_error(h, MMF_ERR_UNSUPPORTED, "%s: top_k %d > %d", who, top_k, MMF_MAX_TOP_K);
+  if (!h->vault_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "%s: no vault loaded", who);
+  if (algo != MMF_ALGO_AUTO && algo != MMF_ALGO_STREAM && algo != MMF_ALGO_MMA)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "%s: unknown algo %d", who, algo);
+  if (n_queries == 0) return MMF_OK;
+  if (h->vault_rows == 0) return mmf_fill_empty(h, n_queries, top_k, out_scores, out_rows, out_packed, out_disc, st);
+  const int64_t chunk = 65536;
+  for (int64_t q0 = 0; q0 < n_queries; q0 += chunk) {
+    const int64_t nq = std::min(chunk, n_queries - q0);
+    bool use_mma;
+    if (algo == MMF_ALGO_MMA) {
+      if (!mmf_mma_supported(h, nq, top_k))
+        return mmf_set_error(h, MMF_ERR_UNSUPPORTED, "%s: tcgen05 path unavailable for this shape", who);
+      use_mma = true;
+    } else if (algo == MMF_ALGO_STREAM) {
+      use_mma = false;
+    } else {
+      use_mma = nq >= 16 && mmf_mma_supported(h, nq, top_k);   // below that the search is HBM-bound on CUDA cores
+    }
+    float* os = out_scores ? out_scores + q0 * top_k : nullptr;
+    int64_t* orow = out_rows ? out_rows + q0 * top_k : nullptr;
+    uint64_t* op = out_packed ? out_packed + q0 * top_k : nullptr;
+    float* od = out_disc ? out_disc + q0 : nullptr;
+    const int rc = use_mma ? mmf_mma_search(h, queries + q0 * MMF_DIM, nq, top_k, threshold, os, orow, op, od, st)
+                           : mmf_stream_search(h, queries + q0 * MMF_DIM, nq, top_k, threshold, os, orow, op, od, st);
+    if (rc != MMF_OK) return rc;
+  }
+  return MMF_OK;
+}
+
+extern "C" int mmf_vault_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                                int algo, float* out_scores, int64_t* out_rows, float* out_discrepancy,
+                                mmf_stream_t stream) {
+  if (h && n_queries > 0 && (!out_scores || !out_rows))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search: null output");
+  return search_dispatch(h, queries, n_queries, top_k, threshold, algo, out_scores, out_rows, nullptr,
+                         out_discrepancy, (cudaStream_t)stream, "vault_search");
+}
+
+extern "C" int mmf_vault_search_candidates(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int algo,
+                                           uint64_t* out_packed, mmf_stream_t stream) {
+  if (h && n_queries > 0 && !out_packed)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_candidates: null output");
+  return search_dispatch(h, queries, n_queries, top_k, 0.0, algo, nullptr, nullptr, out_packed, nullptr,
+                         (cudaStream_t)stream, "vault_search_candidates");
+}
+
+extern "C" int mmf_vault_search_host(mmf_handle* h, const float* queries_host, int64_t n_queries, int top_k,
+                                     double threshold, int algo, float* out_scores_host, int64_t* out_rows_host,
+                                     float* out_discrepancy_host) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n_queries < 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K ||
+      (n_queries > 0 && (!queries_host || !out_scores_host || !out_rows_host)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_host: bad argument");
+  if (!h->vault_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_search_host: no vault loaded");
+  if (n_queries == 0) return MMF_OK;
+  MMF_CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  // pinned staging: [queries | scores | rows | disc]; device I/O buffers mirror it
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  const size_t bq = al((size_t)n_queries * MMF_DIM * 4), bs = al((size_t)n_queries * top_k * 4);
+  const size_t br = al((size_t)n_queries * top_k * 8), bd = al((size_t)n_queries * 4);
+  const size_t total = bq + bs + br + bd;
+  int rc = ensure_pinned(h, total);
+  if (rc != MMF_OK) return rc;
+  if (total > h->io_bytes) {
+    if (h->io) MMF_CUDA_OK(h, cudaFree(h->io));
+    h->io = nullptr;
+    h->io_bytes = 0;
+    MMF_CUDA_OK(h, cudaMalloc(&h->io, total));
+    h->io_bytes = total;
+  }
+  char* hp = (char*)h->pinned;
+  char* dp = (char*)h->io;
+  memcpy(hp, queries_host, (size_t)n_queries * MMF_DIM * 4);
+  MMF_CUDA_OK(h, cudaMemcpyAsync(dp, hp, bq, cudaMemcpyHostToDevice, st));
+  float* d_scores = (float*)(dp + bq);
+  int64_t* d_rows = (int64_t*)(dp + bq + bs);
+  float* d_disc = (float*)(dp + bq + bs + br);
+  rc = search_dispatch(h, (const float*)dp, n_queries, top_k, threshold, algo, d_scores, d_rows, nullptr, d_disc, st,
+                       "vault_search_host");
+  if (rc != MMF_OK) return rc;
+  MMF_CUDA_OK(h, cudaMemcpyAsync(hp + bq, dp + bq, bs + br + bd, cudaMemcpyDeviceToHost, st));
+  MMF_CUDA_OK(h, cudaStreamSynchronize(st));
+  memcpy(out_scores_host, hp + bq, (size_t)n_queries * top_k * 4);
+  memcpy(out_rows_host, hp + bq + bs, (size_t)n_queries * top_k * 8);
+  if (out_discrepancy_host) memcpy(out_discrepancy_host, hp + bq + bs + br, (size_t)n_queries * 4);
+  return MMF_OK;
+}

@@ -1,0 +1,114 @@
+// Shared device helpers: order-preserving score keys, warp reductions, handle layout.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/mmf_b200.h"
+
+#define MMF_DIM 512                 // CLIP ViT-B/32 projection dim (misinfo_forensics.py:78-79)
+#define MMF_SPLIT_SCALE 256.0f      // fp32-exact mode stores v*2^8 as fp16 hi + fp16 lo
+#define MMF_SPLIT_INV_SCALE (1.0f / 256.0f)
+
+namespace mmf {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr u32 FULL = 0xffffffffu;
+
+// ---- total order on scores -------------------------------------------------------------
+// np.argsort(similarities)[-k:][::-1] (misinfo_forensics.py:449): descending score, NaN
+// ranks above everything (argsort puts NaN last), equal scores -> higher row id first
+// (stable ascending sort, reversed).  key64 = okey(score) << 32 | row; larger == better;
+// 0 is reserved for "empty" (okey 0 would be a negative NaN, which is canonicalised away).
+__host__ __device__ __forceinline__ u32 okey(float s) {
+  if (s != s) return 0xFFFFFFFFu;
+  s = s + 0.0f;                                  // -0.0 -> +0.0 (numpy compares them equal)
+#ifdef __CUDA_ARCH__
+  u32 u = __float_as_uint(s);
+#else
+  union { float f; u32 u; } c; c.f = s; u32 u = c.u;
+#endif
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float okey_inv(u32 k) {
+  u32 u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; u32 u; } c; c.u = u; return c.f;
+#endif
+}
+__host__ __device__ __forceinline__ u64 pack_key(float s, u32 row) { return ((u64)okey(s) << 32) | row; }
+
+// the reference evaluates `float(s) > 0.85` in Python double on an fp32 value
+// (misinfo_forensics.py:463-464); NaN fails.
+__device__ __forceinline__ float discrepancy_rule(float top, double threshold) {
+  return ((double)top > threshold) ? top : 0.0f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once data: keep it out of L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+}  // namespace mmf
+
+// ---- handle ----------------------------------------------------------------------------
+struct mmf_handle {
+  int device = -1;
+  int sm_count = 148;
+  std::string last_error;
+  int64_t launches = 0;
+  // vault shard
+  void* vault = nullptr;            // FP32 mode: [n][2][512] fp16 (hi row, lo row); BF16: [n][512] bf16
+  bool vault_loaded = false;
+  int64_t vault_rows = 0;
+  int64_t vault_row_offset = 0;
+  int vault_mode = 0;
+  size_t vault_bytes = 0;
+  // fusion judge
+  float* fusion_params = nullptr;   // device, MMF_FUSION_PARAMS floats, re-laid out (see fusion.cu)
+  bool fusion_loaded = false;
+  // scratch
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  void* pinned = nullptr;          // host staging for the *_host entry points
+  size_t pinned_bytes = 0;
+  void* io = nullptr;              // device mirror of the staging buffer
+  size_t io_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  // TMA descriptors for the tcgen05 path live in vault_mma.cu's state
+  void* mma_state = nullptr;
+};
+
+int mmf_set_error(mmf_handle* h, int status, const char* fmt, ...);
+int mmf_ensure_scratch(mmf_handle* h, size_t bytes, cudaStream_t stream);
+
+#define MMF_CUDA_OK(h, expr)                                                                     \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return mmf_set_error((h), MMF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                  \
+  } while (0)
+
+#define MMF_LAUNCH_OK(h)                                                                         \
+  do {                                                                                           \
+    (h)->launches++;                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                        \
+    if (e__ != cudaSuccess)                                                                      \
+      return mmf_set_error((h), MMF_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                           __FILE__, __LINE__);                                                  \
+  } while (0)

@@ -1,0 +1,122 @@
+// K5: fusion judge -- Linear(5,64)+ReLU (+Dropout=identity in eval) + Linear(64,32)+ReLU +
+// Linear(32,2) + softmax + verdict, one warp per sample, a single launch.
+// Replaces misinfo_forensics.py:83-90,106-108 (fusion_layer / forward_fusion), :587-608
+// (fusion_verdict) and, with a modality mask, the fallback rule of :884-899.
+//
+// 28 B in / 12 B out and 4 864 flop per sample: neither roof is reachable; the point is
+// one launch instead of ~8 and no .item() syncs.  Weights (10 120 B) are staged once per
+// block into shared memory, transposed so lane j reads column j conflict-free; layer-2
+// inputs travel by warp shuffle, so no shared-memory round trip per sample.
+#include "common.cuh"
+
+namespace mmf {
+
+struct FusionSmem {
+  float w0t[5][64];    // w0t[i][j] = W0[j][i]
+  float b0[64];
+  float w3t[64][32];   // w3t[i][j] = W3[j][i]
+  float b3[32];
+  float w5[2][32];
+  float b5[2];
+};
+
+__global__ void __launch_bounds__(256) fusion_judge_kernel(const float* __restrict__ params,
+                                                           const float* __restrict__ x,
+                                                           const unsigned char* __restrict__ modality,
+                                                           long long n, float* __restrict__ out_probs,
+                                                           int* __restrict__ out_verdict,
+                                                           float* __restrict__ out_conf) {
+  __shared__ FusionSmem w;
+  // params: [W0 (64,5) | b0 64 | W3 (32,64) | b3 32 | W5 (2,32) | b5 2]  (nn.Linear: weight (out,in))
+  for (int i = threadIdx.x; i < 320; i += blockDim.x) w.w0t[i % 5][i / 5] = params[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) w.b0[i] = params[320 + i];
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) w.w3t[i % 64][i / 64] = params[384 + i];
+  for (int i = threadIdx.x; i < 32; i += blockDim.x) w.b3[i] = params[2432 + i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) w.w5[i / 32][i % 32] = params[2464 + i];
+  if (threadIdx.x < 2) w.b5[threadIdx.x] = params[2528 + threadIdx.x];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long s = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; s < n; s += warps) {
+    const float xl = (lane < 5) ? x[s * 5 + lane] : 0.f;
+    float xi[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) xi[i] = __shfl_sync(FULL, xl, i);
+    const int mod = modality ? modality[s] : 3;
+    float real, fake;
+    if (mod == 3) {                                   // warp-uniform: one sample per warp
+      float h1a = w.b0[lane], h1b = w.b0[lane + 32];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        h1a = fmaf(w.w0t[i][lane], xi[i], h1a);
+        h1b = fmaf(w.w0t[i][lane + 32], xi[i], h1b);
+      }
+      h1a = fmaxf(h1a, 0.f);
+      h1b = fmaxf(h1b, 0.f);
+      float h2 = w.b3[lane];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h2 = fmaf(w.w3t[i][lane], __shfl_sync(FULL, h1a, i), h2);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) h2 = fmaf(w.w3t[32 + i][lane], __shfl_sync(FULL, h1b, i), h2);
+      h2 = fmaxf(h2, 0.f);
+      const float l0 = warp_sum(w.w5[0][lane] * h2) + w.b5[0];
+      const float l1 = warp_sum(w.w5[1][lane] * h2) + w.b5[1];
+      const float m = fmaxf(l0, l1);                  // torch.softmax(dim=1), :598
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      const float inv = 1.0f / (e0 + e1);
+      real = e0 * inv;
+      fake = e1 * inv;
+      if (l0 != l0 || l1 != l1) real = fake = l0 + l1;   // NaN in -> NaN out, like torch
+    } else {                                          // misinfo_forensics.py:884-899
+      fake = (mod == 1) ? xi[1] : (mod == 2) ? fmaxf(xi[2], xi[4]) : 0.5f;
+      fake = fmaxf(0.0f, fminf(1.0f, fake));
+      real = 1.0f - fake;
+    }
+    if (lane == 0) {
+      const int verdict = fake > 0.5f ? 1 : 0;        // :605
+      out_probs[s * 2 + 0] = real;
+      out_probs[s * 2 + 1] = fake;
+      if (out_verdict) out_verdict[s] = verdict;
+      if (out_conf) out_conf[s] = verdict ? fake : real;
+    }
+  }
+}
+
+}  // namespace mmf
+
+static int fusion_launch(mmf_handle* h, const float* x, const uint8_t* modality, int64_t n, float* out_probs,
+                         int32_t* out_verdict, float* out_conf, cudaStream_t st, const char* who) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n < 0 || (n > 0 && (!x || !out_probs))) return mmf_set_error(h, MMF_ERR_BAD_ARG, "%s: bad argument", who);
+  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "%s: fusion weights not loaded", who);
+  if (n == 0) return MMF_OK;
+  const long long want = (n + 7) / 8;
+  const int grid = (int)(want < (long long)h->sm_count * 4 ? want : (long long)h->sm_count * 4);
+  mmf::fusion_judge_kernel<<<grid, 256, 0, st>>>(h->fusion_params, x, modality, n, out_probs, out_verdict, out_conf);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}
+
+extern "C" int mmf_fusion_load(mmf_handle* h, const float* params_host) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (!params_host) return mmf_set_error(h, MMF_ERR_BAD_ARG, "fusion_load: null params");
+  MMF_CUDA_OK(h, cudaSetDevice(h->device));
+  if (!h->fusion_params) MMF_CUDA_OK(h, cudaMalloc(&h->fusion_params, MMF_FUSION_PARAMS * sizeof(float)));
+  // synchronous on purpose: the trainer mutates the weights in place and calls this again
+  MMF_CUDA_OK(h, cudaMemcpy(h->fusion_params, params_host, MMF_FUSION_PARAMS * sizeof(float), cudaMemcpyHostToDevice));
+  h->fusion_loaded = true;
+  return MMF_OK;
+}
+
+extern "C" int mmf_fusion_forward(mmf_handle* h, const float* x, int64_t n, float* out_probs, int32_t* out_verdict,
+                                  float* out_confidence, mmf_stream_t stream) {
+  return fusion_launch(h, x, nullptr, n, out_probs, out_verdict, out_confidence, (cudaStream_t)stream, "fusion_forward");
+}
+
+extern "C" int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modality, int64_t n,
+                                 float* out_probs, int32_t* out_verdict, float* out_confidence,
+                                 mmf_stream_t stream) {
+  if (h && n > 0 && !modality) return mmf_set_error(h, MMF_ERR_BAD_ARG, "verdict_batch: null modality");
+  return fusion_launch(h, scores, modality, n, out_probs, out_verdict, out_confidence, (cudaStream_t)stream, "verdict_batch");
+}

@@ -1,0 +1,200 @@
+// Streaming top-k building blocks shared by the vault search kernels.
+//
+// Producers never sort.  They keep, per query, an unsorted candidate buffer of packed
+// keys (common.cuh: pack_key) and a threshold tau that is a LOWER BOUND on the current
+// k-th best score; an element is appended only when !(s < tau) (NaN and ties pass).  When
+// a buffer nears capacity one warp compacts it to the exact top-k (warp_compact) and
+// raises tau.  A final block-wide radix select + bitonic sort (block_select_topk) turns
+// any number of candidate lists into the sorted top-k.  Keys are unique (row id in the
+// low word), so the selected set and its order are fully deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace mmf {
+
+// k-th largest of the warp-distributed keys (KPL per lane, 0 = empty); bitwise descent,
+// first on the score word, then (only if several candidates tie on it) on the row word.
+template <int KPL>
+__device__ __forceinline__ u64 warp_kth_largest(const u64 (&key)[KPL], int k) {
+  u32 t_hi = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const u32 cand = t_hi | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int r = 0; r < KPL; ++r) c += ((u32)(key[r] >> 32) >= cand);
+    c = __reduce_add_sync(FULL, c);
+    if (c >= k) t_hi = cand;
+  }
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const u32 hi = (u32)(key[r] >> 32);
+    gt += (hi > t_hi);
+    eq += (hi == t_hi) && key[r] != 0;
+  }
+  gt = __reduce_add_sync(FULL, gt);
+  eq = __reduce_add_sync(FULL, eq);
+  const int need = k - gt;                 // how many of the tied candidates survive
+  u32 t_lo = 0;
+  if (eq > need && t_hi != 0) {            // warp-uniform
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; --bit) {
+      const u32 cand = t_lo | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int r = 0; r < KPL; ++r) c += ((u32)(key[r] >> 32) == t_hi) && ((u32)key[r] >= cand);
+      c = __reduce_add_sync(FULL, c);
+      if (c >= need) t_lo = cand;
+    }
+  }
+  return ((u64)t_hi << 32) | t_lo;
+}
+
+// Compacts buf[0..cnt) (shared or global memory, cnt <= 32*KPL) to its top-k in place.
+// Whole warp participates.  Returns the new count; *tau_out = score of the k-th best when
+// the buffer held >= k candidates (else unchanged).
+template <int KPL>
+__device__ __forceinline__ int warp_compact(u64* buf, int cnt, int k, float* tau_out) {
+  const int lane = threadIdx.x & 31;
+  if (cnt <= k) return cnt;
+  u64 key[KPL];
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const int i = r * 32 + lane;
+    key[r] = (i < cnt) ? buf[i] : 0ull;
+  }
+  __syncwarp();
+  const u64 t = warp_kth_largest<KPL>(key, k);
+  int base = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const bool keep = key[r] >= t && key[r] != 0;
+    const u32 m = __ballot_sync(FULL, keep);
+    if (keep) buf[base + __popc(m & ((1u << lane) - 1))] = key[r];
+    base += __popc(m);
+  }
+  __syncwarp();
+  *tau_out = okey_inv((u32)(t >> 32));
+  return base;
+}
+
+// ---- block-wide exact selection ---------------------------------------------------------
+struct SelectSmem {
+  u32 hist[256];
+  u32 sel_digit, sel_above, n_win;
+  u64 win[MMF_MAX_TOP_K];
+};
+
+// Candidate source: n_lists lists of up to k_in packed keys; list l starts at
+// lists + l*list_stride; if counts != nullptr only the first counts[l*count_stride]
+// entries of list l are valid; key 0 is always skipped.
+struct CandidateLists {
+  const u64* lists;
+  const int* counts;
+  int n_lists;
+  int k_in;
+  long long list_stride;
+  long long count_stride;
+};
+
+// Selects the top_k largest keys and writes them sorted descending.  All threads of the
+// block must call it.  top_k <= MMF_MAX_TOP_K.  Slots beyond the number of valid
+// candidates get score NaN / row -1 / key 0.
+__device__ __forceinline__ void block_select_topk(const CandidateLists& src, int top_k, SelectSmem& sm,
+                                                  float* out_scores, long long* out_rows, u64* out_packed,
+                                                  float* out_disc, double threshold) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const long long total = (long long)src.n_lists * src.k_in;
+  u64 prefix = 0, mask = 0;
+  u32 need = top_k;
+  bool all = false;                           // fewer valid candidates than top_k: take all
+  for (int pass = 7; pass >= 0 && !all; --pass) {
+    for (int i = tid; i < 256; i += nthr) sm.hist[i] = 0;
+    __syncthreads();
+    for (long long i = tid; i < total; i += nthr) {
+      const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
+      if (src.counts && j >= src.counts[l * src.count_stride]) continue;
+      const u64 key = src.lists[l * src.list_stride + j];
+      if (key != 0 && (key & mask) == prefix) atomicAdd(&sm.hist[(key >> (8 * pass)) & 255], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {                           // warp 0: find the digit where the suffix count reaches `need`
+      u32 loc[8], s = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { loc[b] = sm.hist[tid * 8 + b]; s += loc[b]; }
+      u32 incl = s;                           // suffix sum over lanes >= tid
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 v = __shfl_down_sync(FULL, incl, o);
+        if (tid + o < 32) incl += v;
+      }
+      const u32 above_lane = incl - s;        // candidates in higher lanes' bins
+      const u32 tot = __shfl_sync(FULL, incl, 0);
+      if (tot < need) {
+        if (tid == 0) sm.sel_digit = 0xFFFFFFFFu;
+      } else if (above_lane < need && incl >= need) {   // exactly one lane
+        u32 above = above_lane;
+        int d = 7;
+        for (; d >= 0; --d) {
+          if (above + loc[d] >= need) break;
+          above += loc[d];
+        }
+        sm.sel_digit = tid * 8 + d;
+        sm.sel_above = above;
+      }
+    }
+    __syncthreads();
+    if (sm.sel_digit == 0xFFFFFFFFu) {
+      all = true;
+    } else {
+      need -= sm.sel_above;
+      prefix |= (u64)sm.sel_digit << (8 * pass);
+      mask |= 0xFFull << (8 * pass);
+    }
+    __syncthreads();
+  }
+  const u64 t = all ? 1ull : prefix;          // winners: key >= t (keys unique -> exactly top_k of them)
+  // gather winners, pad, bitonic sort descending
+  int kp2 = 1;
+  while (kp2 < top_k) kp2 <<= 1;
+  for (int i = tid; i < kp2; i += nthr) sm.win[i] = 0;
+  if (tid == 0) sm.n_win = 0;
+  __syncthreads();
+  for (long long i = tid; i < total; i += nthr) {
+    const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
+    if (src.counts && j >= src.counts[l * src.count_stride]) continue;
+    const u64 key = src.lists[l * src.list_stride + j];
+    if (key != 0 && key >= t) {
+      const u32 p = atomicAdd(&sm.n_win, 1u);
+      if (p < (u32)top_k) sm.win[p] = key;
+    }
+  }
+  __syncthreads();
+  for (int size = 2; size <= kp2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < kp2; i += nthr) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const u64 a = sm.win[i], b = sm.win[j];
+          const bool desc = ((i & size) == 0);
+          if (desc ? (a < b) : (a > b)) { sm.win[i] = b; sm.win[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < top_k; i += nthr) {
+    const u64 key = sm.win[i];
+    if (out_packed) out_packed[i] = key;
+    if (out_scores) out_scores[i] = key ? okey_inv((u32)(key >> 32)) : __int_as_float(0x7FC00000);
+    if (out_rows) out_rows[i] = key ? (long long)(u32)key : -1ll;
+  }
+  if (tid == 0 && out_disc) {
+    const u64 key = sm.win[0];
+    *out_disc = key ? discrepancy_rule(okey_inv((u32)(key >> 32)), threshold) : 0.0f;
+  }
+  __syncthreads();
+}
+
+}  // namespace mmf

@@ -1,0 +1,345 @@
+// K2: HBM-streaming Truth-Vault search for small query batches (batch-1 latency mode),
+// fused with the top-k so the similarity vector never reaches HBM.
+// Replaces misinfo_forensics.py:446 (similarities = Vn @ q) and :449-450 (argsort top-k).
+//
+// Roofline: HBM.  Algorithmic bytes per query = n_rows * 512 * elem (2.048 GB at 1M rows
+// fp32-exact, 1.024 GB bf16); arithmetic is ~1 FMA per 4 bytes, far below the ridge.
+//
+// Shape: grid = (row ranges, query chunks of QC).  A warp owns whole rows (2 KB, four
+// coalesced 512 B requests per lane-quad), keeps the QC normalised queries in registers
+// and reduces with xor shuffles; per-block candidate buffers + thresholds live in shared
+// memory (topk.cuh), thresholds are shared grid-wide through one atomicMax word per
+// query, and the LAST block to finish a query chunk merges the per-block top-k lists, so
+// one launch produces the final sorted result.
+#include "common.cuh"
+#include "topk.cuh"
+
+#include <algorithm>
+
+namespace mmf {
+
+struct StreamParams {
+  const void* vault;
+  long long n_rows;
+  u32 row_base;
+  const float* qn;        // (n_queries, 512) normalised queries
+  int n_queries;
+  int top_k;
+  long long rows_per_cta; // multiple of 32
+  u32* g_tau;             // (n_queries) shared threshold keys, zeroed by the prep kernel
+  u64* part_keys;         // (gridDim.x, n_queries, top_k)
+  int* part_cnt;          // (gridDim.x, n_queries)
+  u32* done;              // (gridDim.y) arrival counters, self-resetting
+  float* out_scores;
+  long long* out_rows;
+  u64* out_packed;
+  float* out_disc;
+  double threshold;
+};
+
+// One warp per query: q / ||q|| (misinfo_forensics.py:439) + reset of the shared threshold.
+__global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict__ q, int n_queries,
+                                                         float* __restrict__ qn, u32* __restrict__ g_tau) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_queries) return;
+  float v[MMF_DIM / 32], ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < MMF_DIM / 32; ++j) { v[j] = q[(long long)w * MMF_DIM + j * 32 + lane]; ss = fmaf(v[j], v[j], ss); }
+  const float norm = sqrtf(warp_sum(ss));
+#pragma unroll
+  for (int j = 0; j < MMF_DIM / 32; ++j) qn[(long long)w * MMF_DIM + j * 32 + lane] = v[j] / norm;
+  if (lane == 0) g_tau[w] = 0;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8], bool bf16) {
+  const u32 x[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (bf16) {
+      f[2 * i] = __uint_as_float(x[i] << 16);
+      f[2 * i + 1] = __uint_as_float(x[i] & 0xFFFF0000u);
+    } else {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&x[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+}
+
+template <int QC, bool BF16, int KPL>
+__global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamParams p) {
+  constexpr int C = 32 * KPL;          // candidate capacity per query
+  constexpr int LIMIT = C - 64;        // compaction trigger (two 32-row intervals of slack)
+  constexpr int NLD = BF16 ? 2 : 4;    // 128-bit loads per lane per row
+  __shared__ u64 buf[QC][C];
+  __shared__ int cnt[QC];
+  __shared__ volatile float tau[QC];
+  __shared__ u32 tau_key[QC];
+  __shared__ int s_last;
+  __shared__ SelectSmem sel;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.y * QC;
+  const int nq = min(QC, p.n_queries - q0);
+  const int k = p.top_k;
+
+  if (tid < QC) { cnt[tid] = 0; tau[tid] = -INFINITY; tau_key[tid] = 0; }
+
+  // lane owns elements 8*lane..+7 and 256+8*lane..+7 of every row
+  float q[QC][16];
+#pragma unroll
+  for (int qi = 0; qi < QC; ++qi) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      q[qi][e] = (qi < nq) ? p.qn[(long long)(q0 + qi) * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)] : 0.f;
+  }
+  __syncthreads();
+
+  const long long row_begin = (long long)blockIdx.x * p.rows_per_cta;
+  const long long row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  const uint4* vault = reinterpret_cast<const uint4*>(p.vault);
+  constexpr int ROW_U4 = BF16 ? 64 : 128;   // uint4 per stored row
+
+  for (long long base = row_begin; base < row_end; base += 32) {
+    u32 g_seen = 0;
+    if (warp < nq && lane == 0) g_seen = *reinterpret_cast<volatile u32*>(p.g_tau + q0 + warp);
+#pragma unroll
+    for (int sub = 0; sub < 2; ++sub) {
+      const long long r0 = base + sub * 16 + warp * 2;
+      uint4 ld[2][NLD];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (r0 + u < row_end) {
+          const uint4* rp = vault + (r0 + u) * ROW_U4;
+#pragma unroll
+          for (int c = 0; c < NLD; ++c) ld[u][c] = ldg_stream(rp + c * 32 + lane);
+        } else {
+#pragma unroll
+          for (int c = 0; c < NLD; ++c) ld[u][c] = make_uint4(0, 0, 0, 0);
+        }
+      }
+      float acc[2][QC];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float f[8];
+          unpack8(ld[u][c], f, BF16);
+          if (!BF16) {
+            float g[8];
+            unpack8(ld[u][c + 2], g, false);   // lo plane
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] += g[e];   // exact: hi + lo fits 24 bits
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[c * 8 + e] = f[e];
+        }
+#pragma unroll
+        for (int qi = 0; qi < QC; ++qi) {
+          float a = 0.f;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) a = fmaf(v[e], q[qi][e], a);
+          acc[u][qi] = a;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int qi = 0; qi < QC; ++qi) acc[u][qi] = warp_sum(acc[u][qi]);
+      if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (r0 + u < row_end) {
+#pragma unroll
+            for (int qi = 0; qi < QC; ++qi) {
+              if (qi < nq) {
+                const float s = BF16 ? acc[u][qi] : acc[u][qi] * MMF_SPLIT_INV_SCALE;
+                if (!(s < tau[qi])) {
+                  const int pos = atomicAdd(&cnt[qi], 1);
+                  buf[qi][pos] = pack_key(s, p.row_base + (u32)(r0 + u));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // adopt a better threshold found by another block (any block's k-th best is a valid lower bound)
+    if (warp < nq && lane == 0 && g_seen > tau_key[warp]) { tau_key[warp] = g_seen; tau[warp] = okey_inv(g_seen); }
+    // the predicate may miss appends still in flight; LIMIT leaves a second interval of slack
+    const int over = __syncthreads_or(tid < nq && cnt[tid] > LIMIT);
+    if (over) {
+      if (warp < nq && cnt[warp] > k) {
+        float t = 0.f;
+        const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
+        if (lane == 0) {
+          cnt[warp] = c;
+          const u32 tk = okey(t);
+          if (tk > tau_key[warp]) { tau_key[warp] = tk; tau[warp] = t; atomicMax(p.g_tau + q0 + warp, tk); }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (warp < nq) {
+    float t;
+    const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
+    u64* dst = p.part_keys + ((long long)blockIdx.x * p.n_queries + q0 + warp) * k;
+    for (int i = lane; i < c; i += 32) dst[i] = buf[warp][i];
+    if (lane == 0) p.part_cnt[(long long)blockIdx.x * p.n_queries + q0 + warp] = c;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const u32 ticket = atomicAdd(p.done + blockIdx.y, 1u);
+    s_last = (ticket == gridDim.x - 1);
+    if (s_last) p.done[blockIdx.y] = 0;     // self-reset for the next search
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int qi = 0; qi < nq; ++qi) {
+    const long long qg = q0 + qi;
+    CandidateLists src;
+    src.lists = p.part_keys + qg * k;
+    src.counts = p.part_cnt + qg;
+    src.n_lists = gridDim.x;
+    src.k_in = k;
+    src.list_stride = (long long)p.n_queries * k;
+    src.count_stride = p.n_queries;
+    block_select_topk(src, k, sel, p.out_scores ? p.out_scores + qg * k : nullptr,
+                      p.out_rows ? p.out_rows + qg * k : nullptr, p.out_packed ? p.out_packed + qg * k : nullptr,
+                      p.out_disc ? p.out_disc + qg : nullptr, p.threshold);
+  }
+}
+
+// (n_lists, n_queries, k_in) packed candidates -> per-query sorted top-k.  One block per query.
+__global__ void __launch_bounds__(256) topk_merge_kernel(const u64* __restrict__ packed, int n_lists,
+                                                         long long n_queries, int k_in, int top_k, double threshold,
+                                                         float* out_scores, long long* out_rows, u64* out_packed,
+                                                         float* out_disc) {
+  __shared__ SelectSmem sel;
+  const long long qg = blockIdx.x;
+  CandidateLists src;
+  src.lists = packed + qg * k_in;
+  src.counts = nullptr;
+  src.n_lists = n_lists;
+  src.k_in = k_in;
+  src.list_stride = n_queries * k_in;
+  src.count_stride = 0;
+  block_select_topk(src, top_k, sel, out_scores ? out_scores + qg * top_k : nullptr,
+                    out_rows ? out_rows + qg * top_k : nullptr, out_packed ? out_packed + qg * top_k : nullptr,
+                    out_disc ? out_disc + qg : nullptr, threshold);
+}
+
+__global__ void fill_empty_kernel(long long n_queries, int top_k, float* out_scores, long long* out_rows,
+                                  u64* out_packed, float* out_disc) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_queries * top_k) {
+    if (out_scores) out_scores[i] = __int_as_float(0x7FC00000);
+    if (out_rows) out_rows[i] = -1;
+    if (out_packed) out_packed[i] = 0;
+  }
+  if (i < n_queries && out_disc) out_disc[i] = 0.f;
+}
+
+}  // namespace mmf
+
+using namespace mmf;
+
+template <int QC, bool BF16>
+static void launch_stream_k(int kpl, dim3 grid, cudaStream_t st, const StreamParams& p) {
+  if (kpl == 4) vault_stream_topk_kernel<QC, BF16, 4><<<grid, 256, 0, st>>>(p);
+  else if (kpl == 8) vault_stream_topk_kernel<QC, BF16, 8><<<grid, 256, 0, st>>>(p);
+  else vault_stream_topk_kernel<QC, BF16, 16><<<grid, 256, 0, st>>>(p);
+}
+
+template <bool BF16>
+static void launch_stream_q(int qc, int kpl, dim3 grid, cudaStream_t st, const StreamParams& p) {
+  if (qc == 1) launch_stream_k<1, BF16>(kpl, grid, st, p);
+  else if (qc == 2) launch_stream_k<2, BF16>(kpl, grid, st, p);
+  else if (qc == 4) launch_stream_k<4, BF16>(kpl, grid, st, p);
+  else launch_stream_k<8, BF16>(kpl, grid, st, p);
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Streaming search over the resident shard.  Exactly one of (out_scores/out_rows) or out_packed
+// is normally given; any may be null.
+int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                      float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st) {
+  const int Q = (int)n_queries;
+  const int qc = Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8;
+  const int gy = (Q + qc - 1) / qc;
+  const int kpl = top_k <= 64 ? 4 : top_k <= 192 ? 8 : 16;
+  const long long target = (long long)h->sm_count * 3;
+  long long gx = std::max<long long>(1, (target + gy - 1) / gy);
+  gx = std::min<long long>(gx, std::max<long long>(1, (h->vault_rows + 511) / 512));
+  long long rows_per_cta = align_up((size_t)((h->vault_rows + gx - 1) / gx), 32);
+  gx = (h->vault_rows + rows_per_cta - 1) / rows_per_cta;
+
+  // scratch: [done 64 KB | qn | g_tau | part_cnt | part_keys]
+  const size_t off_qn = 65536;
+  const size_t off_tau = off_qn + align_up((size_t)Q * MMF_DIM * 4, 256);
+  const size_t off_cnt = off_tau + align_up((size_t)Q * 4, 256);
+  const size_t off_keys = off_cnt + align_up((size_t)gx * Q * 4, 256);
+  const size_t total = off_keys + (size_t)gx * Q * top_k * 8;
+  int rc = mmf_ensure_scratch(h, total, st);
+  if (rc != MMF_OK) return rc;
+  char* s = (char*)h->scratch;
+  float* qn = (float*)(s + off_qn);
+  u32* g_tau = (u32*)(s + off_tau);
+
+  query_prep_kernel<<<(Q + 7) / 8, 256, 0, st>>>(queries, Q, qn, g_tau);
+  MMF_LAUNCH_OK(h);
+
+  StreamParams p;
+  p.vault = h->vault;
+  p.n_rows = h->vault_rows;
+  p.row_base = (u32)h->vault_row_offset;
+  p.qn = qn;
+  p.n_queries = Q;
+  p.top_k = top_k;
+  p.rows_per_cta = rows_per_cta;
+  p.g_tau = g_tau;
+  p.part_keys = (u64*)(s + off_keys);
+  p.part_cnt = (int*)(s + off_cnt);
+  p.done = (u32*)s;
+  p.out_scores = out_scores;
+  p.out_rows = (long long*)out_rows;
+  p.out_packed = (u64*)out_packed;
+  p.out_disc = out_disc;
+  p.threshold = threshold;
+  dim3 grid((unsigned)gx, (unsigned)gy);
+  if (h->vault_mode == MMF_VAULT_BF16) launch_stream_q<true>(qc, kpl, grid, st, p);
+  else launch_stream_q<false>(qc, kpl, grid, st, p);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}
+
+int mmf_fill_empty(mmf_handle* h, int64_t n_queries, int top_k, float* out_scores, int64_t* out_rows,
+                   uint64_t* out_packed, float* out_disc, cudaStream_t st) {
+  const long long n = std::max<long long>(n_queries * top_k, n_queries);
+  fill_empty_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n_queries, top_k, out_scores, (long long*)out_rows,
+                                                                 (u64*)out_packed, out_disc);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}
+
+extern "C" int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n_queries, int k_in,
+                              int top_k, double threshold, float* out_scores, int64_t* out_rows, float* out_discrepancy,
+                              mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n_lists <= 0 || n_queries < 0 || k_in <= 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K || (n_queries > 0 && !packed))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "topk_merge: bad argument (n_lists=%d n_queries=%lld k_in=%d top_k=%d)",
+                         n_lists, (long long)n_queries, k_in, top_k);
+  if (n_queries == 0) return MMF_OK;
+  topk_merge_kernel<<<(unsigned)n_queries, 256, 0, (cudaStream_t)stream>>>(
+      (const u64*)packed, n_lists, n_queries, k_in, top_k, threshold, out_scores, (long long*)out_rows, nullptr,
+      out_discrepancy);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}
