@@ -109,7 +109,7 @@ def order_key64(scores: np.ndarray, idx: np.ndarray) -> np.ndarray:
 
 def vault_search_batched(vault: np.ndarray, queries: np.ndarray, top_k: int,
                          vault_is_normalised: bool = False, chunk: int = 64,
-                         row_offset: int = 0):
+                         row_offset: int = 0, queries_normalised: bool = False):
     """Batched restatement of misinfo_forensics.py:438-450: per query identical to
     vault_search_as_shipped except that ties / NaN follow order_key64 (the shipped
     np.argsort is unstable, so tie order there is implementation-defined).
@@ -120,7 +120,7 @@ def vault_search_batched(vault: np.ndarray, queries: np.ndarray, top_k: int,
     vn = vault if vault_is_normalised else vault_normalise(vault)
     vn32 = np.ascontiguousarray(vn, dtype=np.float32)   # numpy promotes fp16 @ fp32 -> fp32
     q = torch.as_tensor(np.asarray(queries), dtype=torch.float32).reshape(-1, vault.shape[1])
-    qn = normalise_rows(q).numpy()
+    qn = (q if queries_normalised else normalise_rows(q)).numpy()
     n = vn32.shape[0]
     k = min(int(top_k), n)
     nq = qn.shape[0]
