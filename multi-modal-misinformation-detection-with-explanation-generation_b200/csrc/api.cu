@@ -101,6 +101,7 @@ extern "C" int mmf_destroy(mmf_handle* h) {
   mmf_mma_destroy(h);
   if (h->vault) cudaFree(h->vault);
   if (h->fusion_params) cudaFree(h->fusion_params);
+  if (h->vault_nan_rows_dev) cudaFree(h->vault_nan_rows_dev);
   if (h->scratch) cudaFree(h->scratch);
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->io) cudaFree(h->io);

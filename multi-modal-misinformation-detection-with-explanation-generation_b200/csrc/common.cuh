@@ -75,6 +75,8 @@ struct mmf_handle {
   void* vault = nullptr;            // FP32 mode: [n][2][512] fp16 (hi row, lo row); BF16: [n][512] bf16
   bool vault_loaded = false;
   int64_t vault_rows = 0;
+  int64_t vault_nan_rows = 0;      // zero-norm rows (NaN after normalisation): handled by the streaming kernel only
+  unsigned long long* vault_nan_rows_dev = nullptr;
   int64_t vault_row_offset = 0;
   int vault_mode = 0;
   size_t vault_bytes = 0;

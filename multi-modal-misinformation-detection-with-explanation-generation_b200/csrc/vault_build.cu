@@ -17,7 +17,8 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 // One warp per row; lane owns elements {32*j + lane}.  HBM-bound, run once.
 template <typename T>
 __global__ void __launch_bounds__(256) vault_normalise_kernel(const T* __restrict__ src, long long n_rows, int mode,
-                                                              void* __restrict__ dst, long long dst_row0) {
+                                                              void* __restrict__ dst, long long dst_row0,
+                                                              unsigned long long* __restrict__ nan_rows) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; r < n_rows; r += warps) {
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(256) vault_normalise_kernel(const T* __restric
       ss = fmaf(v[j], v[j], ss);
     }
     const float norm = sqrtf(warp_sum(ss));
+    if (lane == 0 && !(norm > 0.f && norm < INFINITY)) atomicAdd(nan_rows, 1ull);   // row becomes NaN (0/0) like NumPy
     if (mode == MMF_VAULT_BF16) {
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(dst) + (dst_row0 + r) * MMF_DIM;
 #pragma unroll
@@ -61,13 +63,14 @@ static size_t src_elem_size(int dt) {
 
 static int launch_normalise(mmf_handle* h, const void* dev_src, int dt, long long n, int mode, void* dst,
                             long long dst_row0, cudaStream_t st) {
+  unsigned long long* nan_rows = h->vault_nan_rows_dev;
   const long long want = (n + 7) / 8;
   const int grid = (int)std::min<long long>(want, (long long)h->sm_count * 16);
   switch (dt) {
-    case MMF_F32: mmf::vault_normalise_kernel<float><<<grid, 256, 0, st>>>((const float*)dev_src, n, mode, dst, dst_row0); break;
-    case MMF_F16: mmf::vault_normalise_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dev_src, n, mode, dst, dst_row0); break;
-    case MMF_BF16: mmf::vault_normalise_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dev_src, n, mode, dst, dst_row0); break;
-    case MMF_F64: mmf::vault_normalise_kernel<double><<<grid, 256, 0, st>>>((const double*)dev_src, n, mode, dst, dst_row0); break;
+    case MMF_F32: mmf::vault_normalise_kernel<float><<<grid, 256, 0, st>>>((const float*)dev_src, n, mode, dst, dst_row0, nan_rows); break;
+    case MMF_F16: mmf::vault_normalise_kernel<__half><<<grid, 256, 0, st>>>((const __half*)dev_src, n, mode, dst, dst_row0, nan_rows); break;
+    case MMF_BF16: mmf::vault_normalise_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)dev_src, n, mode, dst, dst_row0, nan_rows); break;
+    case MMF_F64: mmf::vault_normalise_kernel<double><<<grid, 256, 0, st>>>((const double*)dev_src, n, mode, dst, dst_row0, nan_rows); break;
   }
   MMF_LAUNCH_OK(h);
   return MMF_OK;
@@ -85,6 +88,7 @@ extern "C" int mmf_vault_unload(mmf_handle* h) {
   h->vault = nullptr;
   h->vault_loaded = false;
   h->vault_rows = 0;
+  h->vault_nan_rows = 0;
   h->vault_bytes = 0;
   h->vault_row_offset = 0;
   return mmf_mma_vault_changed(h);
@@ -120,6 +124,8 @@ extern "C" int mmf_vault_load(mmf_handle* h, const void* rows, int rows_on_devic
     return mmf_set_error(h, MMF_ERR_NOMEM, "vault_load: cannot allocate %zu bytes of HBM", bytes);
   }
   cudaStream_t st = h->own_stream;
+  if (!h->vault_nan_rows_dev) MMF_CUDA_OK(h, cudaMalloc(&h->vault_nan_rows_dev, sizeof(unsigned long long)));
+  MMF_CUDA_OK(h, cudaMemsetAsync(h->vault_nan_rows_dev, 0, sizeof(unsigned long long), st));
   if (rows_on_device) {
     rc = launch_normalise(h, rows, src_dtype, n_rows, vault_mode, h->vault, 0, st);
     if (rc != MMF_OK) return rc;
@@ -143,7 +149,10 @@ extern "C" int mmf_vault_load(mmf_handle* h, const void* rows, int rows_on_devic
     }
     MMF_CUDA_OK(h, cudaFree(stage));
   }
+  unsigned long long nan_rows = 0;
+  MMF_CUDA_OK(h, cudaMemcpyAsync(&nan_rows, h->vault_nan_rows_dev, sizeof nan_rows, cudaMemcpyDeviceToHost, st));
   MMF_CUDA_OK(h, cudaStreamSynchronize(st));
+  h->vault_nan_rows = (int64_t)nan_rows;
   h->vault_loaded = true;
   h->vault_rows = n_rows;
   h->vault_bytes = bytes;
