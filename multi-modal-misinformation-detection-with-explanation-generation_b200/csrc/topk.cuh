@@ -80,10 +80,13 @@ __device__ __forceinline__ int warp_compact(u64* buf, int cnt, int k, float* tau
 }
 
 // ---- block-wide exact selection ---------------------------------------------------------
+#define MMF_SELECT_MAX_LISTS 1024
+
 struct SelectSmem {
   u32 hist[256];
-  u32 sel_digit, sel_above, n_win;
+  u32 sel_digit, sel_above, n_win, n_staged;
   u64 win[MMF_MAX_TOP_K];
+  int counts[MMF_SELECT_MAX_LISTS];
 };
 
 // Candidate source: n_lists lists of up to k_in packed keys; list l starts at
@@ -98,62 +101,120 @@ struct CandidateLists {
   long long count_stride;
 };
 
+// One 8-bit radix-select pass over `n` keys produced by `key_at(i)`: histogram of the digit at
+// `pass` among keys matching (mask, prefix), then the digit where the suffix count reaches `need`.
+// Returns false when there are fewer than `need` keys in total (only possible on the first pass).
+template <typename KeyAt>
+__device__ __forceinline__ bool radix_pass(KeyAt key_at, long long n, int pass, u64& prefix, u64& mask, u32& need,
+                                           SelectSmem& sm) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < 256; i += nthr) sm.hist[i] = 0;
+  __syncthreads();
+  for (long long i = tid; i < n; i += nthr) {
+    const u64 key = key_at(i);
+    if (key != 0 && (key & mask) == prefix) atomicAdd(&sm.hist[(key >> (8 * pass)) & 255], 1u);
+  }
+  __syncthreads();
+  if (tid < 32) {                             // warp 0: find the digit where the suffix count reaches `need`
+    u32 loc[8], s = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) { loc[b] = sm.hist[tid * 8 + b]; s += loc[b]; }
+    u32 incl = s;                             // suffix sum over lanes >= tid
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u32 v = __shfl_down_sync(FULL, incl, o);
+      if (tid + o < 32) incl += v;
+    }
+    const u32 above_lane = incl - s;          // candidates in higher lanes' bins
+    const u32 tot = __shfl_sync(FULL, incl, 0);
+    if (tot < need) {
+      if (tid == 0) sm.sel_digit = 0xFFFFFFFFu;
+    } else if (above_lane < need && incl >= need) {     // exactly one lane
+      u32 above = above_lane;
+      int d = 7;
+      for (; d >= 0; --d) {
+        if (above + loc[d] >= need) break;
+        above += loc[d];
+      }
+      sm.sel_digit = tid * 8 + d;
+      sm.sel_above = above;
+    }
+  }
+  __syncthreads();
+  const u32 digit = sm.sel_digit, above = sm.sel_above;
+  __syncthreads();
+  if (digit == 0xFFFFFFFFu) return false;
+  need -= above;
+  prefix |= (u64)digit << (8 * pass);
+  mask |= 0xFFull << (8 * pass);
+  return true;
+}
+
 // Selects the top_k largest keys and writes them sorted descending.  All threads of the
 // block must call it.  top_k <= MMF_MAX_TOP_K.  Slots beyond the number of valid
 // candidates get score NaN / row -1 / key 0.
-__device__ __forceinline__ void block_select_topk(const CandidateLists& src, int top_k, SelectSmem& sm,
-                                                  float* out_scores, long long* out_rows, u64* out_packed,
-                                                  float* out_disc, double threshold) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+// `staging` (shared memory, `staging_cap` keys) receives the valid candidates in ONE parallel
+// sweep over global memory (counts first, then 32-entry chunks, all loads independent), so
+// the 8 radix passes and the winner gather run out of shared memory; if the candidates do
+// not fit, the passes fall back to re-reading global memory (correct, slower).
+// `min_key`: keys below it are known not to be in the top-k (a published lower bound of the k-th
+// best, e.g. g_tau << 32) and are dropped while staging.
+__device__ __forceinline__ void block_select_topk(const CandidateLists& src, int top_k, SelectSmem& sm, u64* staging,
+                                                  int staging_cap, u64 min_key, float* out_scores, long long* out_rows,
+                                                  u64* out_packed, float* out_disc, double threshold) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
   const long long total = (long long)src.n_lists * src.k_in;
+  const bool small_lists = src.n_lists <= MMF_SELECT_MAX_LISTS;
+  if (tid == 0) sm.n_staged = 0;
+  if (small_lists)
+    for (int l = tid; l < src.n_lists; l += nthr)
+      sm.counts[l] = src.counts ? min(src.counts[l * src.count_stride], src.k_in) : src.k_in;
+  __syncthreads();
+  bool staged = small_lists;
+  if (small_lists) {
+    auto stage = [&](u64 key) {
+      if (key != 0 && key >= min_key) {
+        const u32 pos = atomicAdd(&sm.n_staged, 1u);
+        if (pos < (u32)staging_cap) staging[pos] = key;
+      }
+    };
+    if (src.n_lists * 2 >= nthr) {
+      // many short lists: one thread per list, 8 independent loads in flight per thread
+      for (int l = tid; l < src.n_lists; l += nthr) {
+        const u64* lp = src.lists + l * src.list_stride;
+        const int n = sm.counts[l];
+        for (int j0 = 0; j0 < n; j0 += 8) {
+          u64 key[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) key[e] = (j0 + e < n) ? lp[j0 + e] : 0ull;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) stage(key[e]);
+        }
+      }
+    } else {
+      // few long lists: a warp per 32-entry chunk, coalesced
+      const int chunks_per_list = (src.k_in + 31) >> 5;
+      const int n_chunks = src.n_lists * chunks_per_list;
+      for (int c = tid >> 5; c < n_chunks; c += nthr >> 5) {
+        const int l = c / chunks_per_list, j = (c - l * chunks_per_list) * 32 + lane;
+        stage(j < sm.counts[l] ? src.lists[l * src.list_stride + j] : 0ull);
+      }
+    }
+    __syncthreads();
+    staged = sm.n_staged <= (u32)staging_cap;
+  }
+  const long long n_keys = staged ? (long long)sm.n_staged : total;
+  auto key_at = [&](long long i) -> u64 {
+    if (staged) return staging[i];
+    const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
+    if (src.counts && j >= src.counts[l * src.count_stride]) return 0ull;
+    return src.lists[l * src.list_stride + j];
+  };
+
   u64 prefix = 0, mask = 0;
   u32 need = top_k;
   bool all = false;                           // fewer valid candidates than top_k: take all
-  for (int pass = 7; pass >= 0 && !all; --pass) {
-    for (int i = tid; i < 256; i += nthr) sm.hist[i] = 0;
-    __syncthreads();
-    for (long long i = tid; i < total; i += nthr) {
-      const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
-      if (src.counts && j >= src.counts[l * src.count_stride]) continue;
-      const u64 key = src.lists[l * src.list_stride + j];
-      if (key != 0 && (key & mask) == prefix) atomicAdd(&sm.hist[(key >> (8 * pass)) & 255], 1u);
-    }
-    __syncthreads();
-    if (tid < 32) {                           // warp 0: find the digit where the suffix count reaches `need`
-      u32 loc[8], s = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) { loc[b] = sm.hist[tid * 8 + b]; s += loc[b]; }
-      u32 incl = s;                           // suffix sum over lanes >= tid
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u32 v = __shfl_down_sync(FULL, incl, o);
-        if (tid + o < 32) incl += v;
-      }
-      const u32 above_lane = incl - s;        // candidates in higher lanes' bins
-      const u32 tot = __shfl_sync(FULL, incl, 0);
-      if (tot < need) {
-        if (tid == 0) sm.sel_digit = 0xFFFFFFFFu;
-      } else if (above_lane < need && incl >= need) {   // exactly one lane
-        u32 above = above_lane;
-        int d = 7;
-        for (; d >= 0; --d) {
-          if (above + loc[d] >= need) break;
-          above += loc[d];
-        }
-        sm.sel_digit = tid * 8 + d;
-        sm.sel_above = above;
-      }
-    }
-    __syncthreads();
-    if (sm.sel_digit == 0xFFFFFFFFu) {
-      all = true;
-    } else {
-      need -= sm.sel_above;
-      prefix |= (u64)sm.sel_digit << (8 * pass);
-      mask |= 0xFFull << (8 * pass);
-    }
-    __syncthreads();
-  }
+  for (int pass = 7; pass >= 0 && !all; --pass) all = !radix_pass(key_at, n_keys, pass, prefix, mask, need, sm);
   const u64 t = all ? 1ull : prefix;          // winners: key >= t (keys unique -> exactly top_k of them)
   // gather winners, pad, bitonic sort descending
   int kp2 = 1;
@@ -161,13 +222,11 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
   for (int i = tid; i < kp2; i += nthr) sm.win[i] = 0;
   if (tid == 0) sm.n_win = 0;
   __syncthreads();
-  for (long long i = tid; i < total; i += nthr) {
-    const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
-    if (src.counts && j >= src.counts[l * src.count_stride]) continue;
-    const u64 key = src.lists[l * src.list_stride + j];
+  for (long long i = tid; i < n_keys; i += nthr) {
+    const u64 key = key_at(i);
     if (key != 0 && key >= t) {
-      const u32 p = atomicAdd(&sm.n_win, 1u);
-      if (p < (u32)top_k) sm.win[p] = key;
+      const u32 pos = atomicAdd(&sm.n_win, 1u);
+      if (pos < (u32)top_k) sm.win[pos] = key;
     }
   }
   __syncthreads();

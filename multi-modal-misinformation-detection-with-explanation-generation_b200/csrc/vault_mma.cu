@@ -2,22 +2,25 @@
 // top-k fused into the epilogue so the (queries x rows) score matrix never leaves the SM.
 // Replaces the batched form of misinfo_forensics.py:446 (Vn @ q) and :449-450 (argsort top-k).
 //
-// Operands (K-major, 128B-swizzled tiles of [rows][64 elements], 128 B per row, fed by TMA):
-//   A = queries (M = 128 per tile), normalised by the prep kernel.  The query tile of a strip
-//       is RESIDENT on the SM (the v1 kernel streamed it with every vault tile and was bound
-//       by L2->SM operand traffic): 8 k-block tiles = 128 KB of shared memory.
-//   B = vault rows, streamed from HBM through a 3-stage mbarrier ring.
-//   MMF_VAULT_BF16: one bf16 plane each, N = 256 rows per tile, 4 UMMA (K=16) per k-block.
+// Operands.  Measured on B200: with cta_group::1 an SS-form UMMA (both operands in shared memory)
+// is bound by the smem->tensor-core path (~72 B/clk: 128x128x16 takes ~116 clk, 128x256x16 ~170
+// clk), while the TS form (A in TENSOR MEMORY) runs at the 64-clk floor.  So:
+//   A = queries (M = 128 per tile), normalised by the prep kernel, RESIDENT on the SM per strip:
+//       plane 0 (bf16 q, or fp16 qh) lives in tensor memory: 256 columns, written once per
+//       strip by the epilogue threads with tcgen05.st (lane = query, 2 elements per column);
+//       fp32-exact mode also keeps plane 1 (ql, 128 KB) in shared memory, loaded by TMA.
+//   B = vault rows (N = 128 per tile), K-major 128B-swizzled [128][64] tiles streamed from HBM by
+//       TMA through an mbarrier ring (12 x 16 KB in bf16 mode; 3 x 32 KB next to ql otherwise).
+//   MMF_VAULT_BF16: D += q.v, 4 TS-UMMA (K=16) per 64-wide k-block.
 //   MMF_VAULT_FP32: fp32-exact.  x*2^8 = hi + lo (two fp16 planes, 22+ bits), and
-//       q.v * 2^16 = qh.vh + ql.vh + qh.vl  (+ ql.vl, < 2^-22 relative, dropped)
-//     -> 12 UMMA per k-block (N = 128), all into ONE fp32 TMEM accumulator; scores = D*2^-16.
-//     qh is the smem-resident A operand; ql (another 128 KB) lives in TENSOR MEMORY
-//     (256 columns, written once per strip with tcgen05.st) and feeds the TS-form MMA.
+//       q.v * 2^16 = qh.vh + qh.vl + ql.vh  (+ ql.vl, < 2^-22 relative, dropped)
+//     -> 8 TS + 4 SS UMMA per k-block, all into ONE fp32 TMEM accumulator; scores = D * 2^-16.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one elected
-// lane), warps 2-5 = epilogue.  Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a
-// double-buffered TMEM accumulator (tmem_full/tmem_empty, MMA <-> epilogue), so the epilogue of
-// tile i overlaps the MMAs of tile i+1.  TMEM: 2 x N accumulator columns (+ 256 for ql) = 512.
+// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (whole warp runs
+// the loop in the uniform datapath, one elected lane issues), warps 2-9 = epilogue.  Pipelines:
+// smem ring (full/empty mbarriers, TMA <-> MMA) and a double-buffered TMEM accumulator
+// (tmem_full/tmem_empty, MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile
+// i+1.  TMEM: 2 x 128 accumulator columns + 256 operand columns = 512.
 //
 // Epilogue = streaming top-k.  TMEM lane == query, so each epilogue thread owns one query:
 // it reads 32 accumulator columns at a time (tcgen05.ld 32x32b.x32), compares them with its
@@ -31,6 +34,8 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <new>
 
 namespace mmf {
@@ -38,12 +43,19 @@ namespace mmf {
 constexpr int TILE_M = 128;          // queries per tile   (UMMA M)
 constexpr int KBLK = 64;             // elements per k-block: 128 B rows, one 128B-swizzle atom
 constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB: [128 rows][64 elements]
+constexpr int TILE_N = 128;          // vault rows per tile (UMMA N); 2 accumulator buffers = 256 TMEM columns
 constexpr int Q_RESIDENT_BYTES = (MMF_DIM / KBLK) * TILE_BYTES;   // 128 KB
-constexpr int MMA_STAGES = 3;
-constexpr int STAGE_BYTES = 2 * TILE_BYTES;  // 32 KB: bf16 [256][64], or fp16 hi [128][64] + lo [128][64]
-__host__ __device__ constexpr int tile_n(bool split) { return split ? 128 : 256; }
+// smem: bf16 mode = 12 stages x 16 KB; fp32-exact = resident ql (128 KB) + 3 stages x (vh + vl = 32 KB)
+__host__ __device__ constexpr int mma_stages(bool split) { return split ? 3 : 12; }
+__host__ __device__ constexpr int stage_bytes(bool split) { return split ? 2 * TILE_BYTES : TILE_BYTES; }
+__host__ __device__ constexpr int mma_smem_bytes(bool split) {
+  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split) * stage_bytes(split);
+}
 constexpr int NUM_KBLK = MMF_DIM / KBLK;     // 8
-constexpr int MMA_THREADS = 192;
+constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter: a lone warp per scheduler cannot hide its own latency
+constexpr int PRODUCER_WARP = EPI_WARPS;      // warps 0-7: epilogue (warp%4 = TMEM lane quarter), 8: TMA producer,
+constexpr int MMA_WARP = EPI_WARPS + 1;       // 9: MMA issuer -- the highest warp id on its scheduler, so it wins arbitration
+constexpr int MMA_THREADS = 64 + 32 * EPI_WARPS;
 
 struct MmaParams {
   int n_queries;           // valid queries
@@ -53,10 +65,12 @@ struct MmaParams {
   int top_k;
   int q_tiles, v_tiles;
   long long units;         // q_tiles * v_tiles
-  u64* cand;               // [strip][TILE_M][C]
-  int* cand_cnt;           // [strip][TILE_M]
+  u64* cand;               // [strip][2 column halves][TILE_M][C]
+  int* cand_cnt;           // [strip][2][TILE_M]
+  u32* g_tau;              // [q_pad] best known lower bound of each query's k-th best (score key), shared grid-wide
   float inv_scale;         // accumulator -> score
-  const uint4* q_lo;       // fp32-exact mode: the lo plane of the query operand ([q_pad][512] fp16)
+  int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
+  const uint4* q_plane0;   // plane 0 of the query operand ([q_pad][512] bf16, or fp16 hi): goes to tensor memory
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------
@@ -80,6 +94,19 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// for long waits (epilogue waiting for a whole tile of MMAs): back off between polls -- every poll is a
+// shared-memory transaction, and shared-memory bandwidth is what the tensor core's operand fetch needs
+__device__ __forceinline__ void mbar_wait_relaxed(u64* bar, u32 parity) {
+  u32 done;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -93,6 +120,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// one lane of a converged warp (always the same one, so tcgen05.commit sees that lane's MMAs)
+__device__ __forceinline__ bool elect_one() {
+  u32 pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -141,6 +175,11 @@ __device__ __forceinline__ void tmem_ld32(u32 taddr, u32 (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8(u32 taddr, u32 (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO = 1
@@ -157,10 +196,12 @@ __host__ __device__ constexpr u32 umma_idesc(u32 fmt, u32 m, u32 n) {
 // One warp per padded query row: q / ||q|| (misinfo_forensics.py:439), then the MMA operand
 // planes: bf16 (1 plane) or fp16 hi/lo of q*2^8 (2 planes, plane p at row p*q_pad + i).
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
-                                                             int split, void* __restrict__ planes) {
+                                                             int split, void* __restrict__ planes,
+                                                             u32* __restrict__ g_tau) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
+  if (lane == 0) g_tau[w] = 0;
   float v[MMF_DIM / 32], ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MMF_DIM / 32; ++j) {
@@ -190,40 +231,40 @@ template <bool SPLIT, int KPL>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
-  constexpr int TILE_N = tile_n(SPLIT);
-  constexpr int STAGES = MMA_STAGES;
+  constexpr int STAGES = mma_stages(SPLIT);
+  constexpr int STAGE_BYTES = stage_bytes(SPLIT);
   constexpr int C = 32 * KPL;
   constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M, TILE_N);
-  constexpr u32 QL_COL = 2 * TILE_N;                 // fp32-exact: TMEM columns [256,512) hold ql
+  constexpr u32 QA_COL = 2 * TILE_N;                 // TMEM columns [256,512): plane 0 of the query tile
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  unsigned char* q_smem = smem;                                   // resident query tile (qh / bf16)
-  unsigned char* stage_smem = smem + Q_RESIDENT_BYTES;
+  unsigned char* q_smem = smem;                                   // fp32-exact: resident ql tile
+  unsigned char* stage_smem = smem + (SPLIT ? Q_RESIDENT_BYTES : 0);
   u64* full_bar = reinterpret_cast<u64*>(stage_smem + STAGES * STAGE_BYTES);
   u64* empty_bar = full_bar + STAGES;
   u64* tmem_full = empty_bar + STAGES;
   u64* tmem_empty = tmem_full + 2;
-  u64* q_full = tmem_empty + 2;       // producer -> MMA: resident query tile landed
+  u64* q_full = tmem_empty + 2;       // producer -> MMA: resident ql tile landed (fp32-exact)
   u64* q_empty = q_full + 1;          // MMA -> producer: every MMA of the previous strip retired
-  u64* ql_full = q_empty + 1;         // epilogue -> MMA: ql written to TMEM
-  u32* tmem_slot = reinterpret_cast<u32*>(ql_full + 1);
+  u64* qa_full = q_empty + 1;         // epilogue -> MMA: plane 0 written to tensor memory
+  u32* tmem_slot = reinterpret_cast<u32*>(qa_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long u0 = (long long)blockIdx.x * p.units / gridDim.x;
   const long long u1 = (long long)(blockIdx.x + 1) * p.units / gridDim.x;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, EPI_WARPS); }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(ql_full, 4);
+    mbar_init(qa_full, EPI_WARPS);
     fence_barrier_init();
   }
-  if (warp == 1) {   // the whole tensor memory: accumulators (+ ql)
+  if (warp == MMA_WARP) {   // the whole tensor memory: accumulators + query operand
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -232,26 +273,27 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   tcgen05_fence_after();
   const u32 tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ===== TMA producer =====
     if (lane == 0) {
       u32 it = 0, strip = 0;
       int cur_qt = -1;
-      for (long long u = u0; u < u1; ++u) {
-        const int qt = (int)(u / p.v_tiles);
-        const int vt = (int)(u % p.v_tiles);
-        if (qt != cur_qt) {                           // new strip: (re)load the resident query tile
+      int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+      for (long long u = u0; u < u1; ++u, ++vt) {
+        if (vt == p.v_tiles) { vt = 0; ++qt; }
+        if (SPLIT && qt != cur_qt) {                  // new strip: (re)load the resident ql tile (plane 1)
           cur_qt = qt;
           mbar_wait(q_empty, (strip & 1) ^ 1);
           mbar_expect_tx(q_full, Q_RESIDENT_BYTES);
           for (int kb = 0; kb < NUM_KBLK; ++kb)
-            tma_load_2d(q_smem + kb * TILE_BYTES, &tm_a, q_full, kb * KBLK, qt * TILE_M);
+            tma_load_2d(q_smem + kb * TILE_BYTES, &tm_a, q_full, kb * KBLK, p.q_pad + qt * TILE_M);
           ++strip;
         }
         for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);
+          mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
           unsigned char* st = stage_smem + s * STAGE_BYTES;
+          if (p.debug & 2) { mbar_arrive(full_bar + s); continue; }
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
           if (SPLIT) {
             tma_load_3d(st, &tm_b, full_bar + s, kb * KBLK, 0, vt * TILE_N);
@@ -262,50 +304,73 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    // The WHOLE warp runs the loop so that addresses and descriptors are computed once, in the
+    // uniform datapath; only the tcgen05 instructions themselves are issued by the elected lane.
+    {
       u32 it = 0, tile = 0, strip = 0;
       int cur_qt = -1;
       const u32 q_addr = smem_u32(q_smem);
-      for (long long u = u0; u < u1; ++u, ++tile) {
-        const int qt = (int)(u / p.v_tiles);
+      const u32 st_addr = smem_u32(stage_smem);
+      const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
+      const long long t_begin = clock64();
+      int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+      for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
+        if (vt == p.v_tiles) { vt = 0; ++qt; }
         if (qt != cur_qt) {
           cur_qt = qt;
-          mbar_wait(q_full, strip & 1);
-          if (SPLIT) mbar_wait(ql_full, strip & 1);
+          if (SPLIT) mbar_wait(q_full, strip & 1);
+          mbar_wait(qa_full, strip & 1);
           ++strip;
         }
         const u32 acc = tile & 1;
-        mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
+        if (!(p.debug & 4)) mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const u32 d_tmem = tmem_base + acc * TILE_N;
+#pragma unroll 1
         for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(full_bar + s, (it / STAGES) & 1);
+          if (!(p.debug & 4)) mbar_wait(full_bar + s, (it / STAGES) & 1);
           tcgen05_fence_after();
-          const u32 qa = q_addr + kb * TILE_BYTES;
-          const u32 sb = smem_u32(stage_smem + s * STAGE_BYTES);
+          const u64 ql = desc_hi | (u64)(((q_addr + kb * TILE_BYTES) >> 4) & 0x3FFF);
+          const u64 vb = desc_hi | (u64)(((st_addr + s * STAGE_BYTES) >> 4) & 0x3FFF);
+          const u32 qa = tmem_base + QA_COL + kb * (KBLK / 2);     // 2 elements per column
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < KBLK / 16; ++k)          // qh.vh  (bf16 mode: q.v)
-            umma_f16(d_tmem, umma_smem_desc(qa + k * 32), umma_smem_desc(sb + k * 32), IDESC, (kb | k) != 0);
-          if (SPLIT) {
+            for (int k = 0; k < KBLK / 16; ++k)        // qh.vh  (bf16 mode: q.v); A from tensor memory
+              umma_f16_ts(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
+            if (SPLIT) {
 #pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k)        // ql.vh, ql from tensor memory
-              umma_f16_ts(d_tmem, tmem_base + QL_COL + kb * (KBLK / 2) + k * 8, umma_smem_desc(sb + k * 32), IDESC, 1);
+              for (int k = 0; k < KBLK / 16; ++k)      // qh.vl
+                umma_f16_ts(d_tmem, qa + k * 8, vb + (TILE_BYTES >> 4) + 2 * k, IDESC, 1);
 #pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k)        // qh.vl
-              umma_f16(d_tmem, umma_smem_desc(qa + k * 32), umma_smem_desc(sb + TILE_BYTES + k * 32), IDESC, 1);
+              for (int k = 0; k < KBLK / 16; ++k)      // ql.vh, ql from shared memory (+2 = 32 B = 16 elements)
+                umma_f16(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+            }
+            umma_commit(empty_bar + s);               // smem slot free once these MMAs retire
+            if (kb == NUM_KBLK - 1) {
+              umma_commit(tmem_full + acc);           // accumulator complete -> epilogue
+              if (SPLIT && (u + 1 == u1 || vt + 1 == p.v_tiles)) umma_commit(q_empty);   // strip done
+            }
           }
-          umma_commit(empty_bar + s);                 // smem slot free once these MMAs retire
+          __syncwarp();
         }
-        umma_commit(tmem_full + acc);                 // accumulator complete -> epilogue
-        if (u + 1 == u1 || (int)((u + 1) / p.v_tiles) != qt) umma_commit(q_empty);   // strip done
+      }
+      if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
+        mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
+        const long long dt = clock64() - t_begin;
+        printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block\n", tile, it,
+               dt, (double)dt / it);
       }
     }
   } else {
     // ===== epilogue: thread == query (TMEM lane), streaming top-k =====
-    const int quarter = warp & 3;                     // TMEM lanes a warp may touch: 32*(warp%4)..+31
+    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quarter and
+    // split the accumulator columns (32-column chunks of alternating parity).  Each thread keeps its
+    // own candidate list + threshold for its (query, column half).
+    const int quarter = warp & 3;
+    const int half = warp >> 2;
     const int m = quarter * 32 + lane;
     const u32 lane_base = tmem_base + ((u32)(quarter * 32) << 16);
     const int k = p.top_k;
@@ -314,107 +379,126 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     int cnt = 0;
     int cur_qt = -1;
     u64* buf = nullptr;
+    int* cnt_out = nullptr;
+    u32* g_tau = nullptr;
     bool valid_q = false;
     u32 tile = 0;
-    for (long long u = u0; u < u1; ++u, ++tile) {
-      const int qt = (int)(u / p.v_tiles);
-      const int vt = (int)(u % p.v_tiles);
+    int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+    for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
+      if (vt == p.v_tiles) { vt = 0; ++qt; }
       if (qt != cur_qt) {                             // new strip: flush the old one, reset state
-        if (cur_qt >= 0) p.cand_cnt[(long long)(blockIdx.x + cur_qt) * TILE_M + m] = cnt;
+        if (cur_qt >= 0) *cnt_out = cnt;
         cur_qt = qt;
         cnt = 0;
         tau_acc = -INFINITY;
-        buf = p.cand + ((long long)(blockIdx.x + qt) * TILE_M + m) * C;
+        const long long list = ((long long)(blockIdx.x + qt) * 2 + half) * TILE_M + m;
+        buf = p.cand + list * C;
+        cnt_out = p.cand_cnt + list;
+        g_tau = p.g_tau + qt * TILE_M + m;
         valid_q = (qt * TILE_M + m) < p.n_queries;
-        if (SPLIT) {
-          // this thread's query row of the lo plane -> its TMEM lane, 2 fp16 per column.  Every
-          // MMA of the previous strip has retired (its last accumulator was consumed above).
-          const uint4* src = p.q_lo + (long long)(qt * TILE_M + m) * (MMF_DIM * 2 / 16);
+        {
+          // this thread's query row of plane 0 -> its TMEM lane, 2 elements per column (each warp of
+          // a quarter writes half of the 256 columns).  Every MMA of the previous strip has retired:
+          // its last accumulator was consumed above.
+          const uint4* src = p.q_plane0 + (long long)(qt * TILE_M + m) * (MMF_DIM * 2 / 16);
 #pragma unroll 1
-          for (int c = 0; c < MMF_DIM / 64; ++c) {
+          for (int c = half * 4; c < half * 4 + 4; ++c) {
             u32 w[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 x = __ldg(src + c * 8 + i);
               w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
             }
-            tmem_st32(lane_base + QL_COL + c * 32, w);
+            tmem_st32(lane_base + QA_COL + c * 32, w);
           }
           tmem_wait_st();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(ql_full);
+          if (lane == 0) mbar_arrive(qa_full);
         }
       }
+      // a tighter bound found by any other block / warp for this query (valid for every list of it);
+      // issued before the wait so its latency hides behind the MMAs
+      const u32 g_seen = *reinterpret_cast<volatile u32*>(g_tau);
       const u32 acc = tile & 1;
-      mbar_wait(tmem_full + acc, (tile >> 1) & 1);
+      mbar_wait_relaxed(tmem_full + acc, (tile >> 1) & 1);
       tcgen05_fence_after();
+      if (g_seen) tau_acc = fmaxf(tau_acc, okey_inv(g_seen) * acc_scale);
       const long long row0 = (long long)vt * TILE_N;
       const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
+      const bool partial = n_cols < TILE_N;           // beyond n_cols the tile is TMA zero fill
+      const u32 row_id0 = p.row_base + (u32)row0;
 #pragma unroll 1
-      for (int c = 0; c < TILE_N / 32; ++c) {
+      for (int c = half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += 2) {
         u32 v[32];
-        tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
-        tmem_wait_ld();
-        // fast path (almost always): is the chunk maximum below the threshold?  A max tree keeps the
-        // dependent chain at 5 instead of 32 -- one lone warp per scheduler cannot hide latency.
-        // (fmaxf drops NaN next to a number; vaults with NaN rows never reach this kernel.)
+        if (p.debug & 16) {                            // triage: no TMEM read
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0xff800000u;
+        } else {
+          tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
+          tmem_wait_ld();
+        }
+        if (p.debug & 32) continue;                    // triage: TMEM read only
+        // fast path (almost always): chunk maximum below the threshold.  A max tree keeps the
+        // dependent chain short.  (fmaxf drops a NaN next to a number; vaults with NaN rows never
+        // reach this kernel, see mmf_mma_supported.)
         float mx[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        if (!(m8 < tau_acc) && valid_q) {
-          u32 mask = 0;
+        // slow path, warp-uniform and deliberately SMALL in code: the MMA warp's issue loop is latency
+        // critical and a large unrolled epilogue evicts it from the instruction cache (measured: +300
+        // clk per k-block).  Re-read the chunk 8 columns at a time and append the survivors.
+        if (__any_sync(FULL, !(m8 < tau_acc) && valid_q)) {
+#pragma unroll 1
+          for (int g = 0; g < 4; ++g) {
+            u32 w[8];
+            tmem_ld8(lane_base + acc * TILE_N + c * 32 + g * 8, w);
+            tmem_wait_ld();
+            if (valid_q) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mask |= (!(__uint_as_float(v[j]) < tau_acc) ? 1u : 0u) << j;
-          const int lim = n_cols - c * 32;            // columns >= lim are TMA zero fill, not vault rows
-          if (lim < 32) mask &= (lim <= 0) ? 0u : ((1u << lim) - 1u);
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            // v[j] without dynamic register indexing: 5-level select tree
-            u32 t16[16], t8[8], t4[4], t2[2];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) t2[i] = (j & 8) ? t4[2 * i + 1] : t4[2 * i];
-            const float a = __uint_as_float((j & 16) ? t2[1] : t2[0]);
-            buf[cnt++] = pack_key(a * p.inv_scale, p.row_base + (u32)(row0 + c * 32 + j));
+              for (int e = 0; e < 8; ++e) {
+                const float a = __uint_as_float(w[e]);
+                const int col = c * 32 + g * 8 + e;
+                if (!(a < tau_acc) && (!partial || col < n_cols)) buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
+              }
+            }
           }
-        }
-        // keep room for the next 32 columns; compaction is warp-cooperative, one query at a time
-        u32 need = __ballot_sync(FULL, cnt > C - 32);
-        while (need) {
-          const int src = __ffs(need) - 1;
-          need &= need - 1;
-          u64* b = reinterpret_cast<u64*>(__shfl_sync(FULL, reinterpret_cast<u64>(buf), src));
-          const int n = __shfl_sync(FULL, cnt, src);
-          __syncwarp();
-          float t = 0.f;
-          const int kept = warp_compact<KPL>(b, n, k, &t);
-          if (lane == src) {
-            cnt = kept;
-            tau_acc = fmaxf(tau_acc, t * acc_scale);
-          }
-          __syncwarp();
         }
       }
+      // hand the accumulator back FIRST: compaction below then overlaps the next tile's MMAs instead
+      // of stalling them (the slowest of the 8 warps gates tmem_empty)
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty + acc);
+      // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
+      constexpr int ROOM = 32 * (TILE_N / 32 / 2);
+      static_assert(C - ROOM >= 32, "candidate capacity too small for a tile");
+      u32 need = __ballot_sync(FULL, cnt > C - ROOM);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        u64* b = reinterpret_cast<u64*>(__shfl_sync(FULL, reinterpret_cast<u64>(buf), src));
+        const int n = __shfl_sync(FULL, cnt, src);
+        __syncwarp();
+        float t = 0.f;
+        const int kept = warp_compact<KPL>(b, n, k, &t);
+        if (lane == src) {
+          cnt = kept;
+          tau_acc = fmaxf(tau_acc, t * acc_scale);
+          if (t == t) atomicMax(g_tau, okey(t));
+        }
+        __syncwarp();
+      }
     }
-    if (cur_qt >= 0) p.cand_cnt[(long long)(blockIdx.x + cur_qt) * TILE_M + m] = cnt;
+    if (cur_qt >= 0) *cnt_out = cnt;
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
@@ -427,6 +511,7 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int g
                                                         float* out_disc) {
   constexpr int C = 32 * KPL;
   __shared__ SelectSmem sel;
+  __shared__ u64 staging[4096];
   __shared__ int s_first, s_count;
   const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
@@ -445,13 +530,13 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int g
   }
   __syncthreads();
   CandidateLists src;
-  src.lists = p.cand + ((long long)(s_first + qt) * TILE_M + m) * C;
-  src.counts = p.cand_cnt + (long long)(s_first + qt) * TILE_M + m;
-  src.n_lists = s_count;
+  src.lists = p.cand + ((long long)(s_first + qt) * 2 * TILE_M + m) * C;     // [strip][half][m][C]
+  src.counts = p.cand_cnt + (long long)(s_first + qt) * 2 * TILE_M + m;
+  src.n_lists = 2 * s_count;
   src.k_in = C;
   src.list_stride = (long long)TILE_M * C;
   src.count_stride = TILE_M;
-  block_select_topk(src, p.top_k, sel, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+  block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
                     threshold);
@@ -505,13 +590,13 @@ int mmf_mma_vault_changed(mmf_handle* h) {
   if (h->vault_mode == MMF_VAULT_BF16) {
     const cuuint64_t dims[2] = {MMF_DIM, (cuuint64_t)h->vault_rows};
     const cuuint64_t strides[1] = {MMF_DIM * 2};
-    const cuuint32_t box[2] = {KBLK, (cuuint32_t)tile_n(false)};
+    const cuuint32_t box[2] = {KBLK, TILE_N};
     s->vault_map_ok = encode_map(s, &s->tm_vault, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->vault, dims, strides, box);
   } else {
     // [row][plane][512] fp16 viewed as (k, plane, row)
     const cuuint64_t dims[3] = {MMF_DIM, 2, (cuuint64_t)h->vault_rows};
     const cuuint64_t strides[2] = {MMF_DIM * 2, MMF_DIM * 4};
-    const cuuint32_t box[3] = {KBLK, 1, (cuuint32_t)tile_n(true)};
+    const cuuint32_t box[3] = {KBLK, 1, TILE_N};
     s->vault_map_ok = encode_map(s, &s->tm_vault, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->vault, dims, strides, box);
   }
   return MMF_OK;
@@ -532,7 +617,7 @@ void mmf_mma_destroy(mmf_handle* h) {
 template <bool SPLIT, int KPL>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int grid, double threshold,
                       float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st) {
-  const int smem = Q_RESIDENT_BYTES + MMA_STAGES * STAGE_BYTES + 256 + 1024;
+  const int smem = mma_smem_bytes(SPLIT) + 256 + 1024;
   auto kern = vault_mma_topk_kernel<SPLIT, KPL>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   kern<<<grid, MMA_THREADS, smem, st>>>(tm_q, s->tm_vault, p);
@@ -560,8 +645,9 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.n_rows = h->vault_rows;
   p.row_base = (u32)h->vault_row_offset;
   p.top_k = top_k;
-  p.v_tiles = (int)((h->vault_rows + tile_n(split) - 1) / tile_n(split));
+  p.v_tiles = (int)((h->vault_rows + TILE_N - 1) / TILE_N);
   p.units = (long long)p.q_tiles * p.v_tiles;
+  { const char* e = getenv("MMF_MMA_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.inv_scale = split ? (MMF_SPLIT_INV_SCALE * MMF_SPLIT_INV_SCALE) : 1.0f;
   const int grid = (int)std::min<long long>(h->sm_count, p.units);
   const long long strips = (long long)grid + p.q_tiles;
@@ -569,18 +655,20 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   // scratch: [64 KB counters (stream kernel) | query planes | cand_cnt | cand]
   auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   const size_t off_q = 65536;
-  const size_t off_cnt = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
-  const size_t off_cand = off_cnt + al((size_t)strips * TILE_M * 4);
-  const size_t total = off_cand + (size_t)strips * TILE_M * C * 8;
+  const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
+  const size_t off_cnt = off_tau + al((size_t)p.q_pad * 4);
+  const size_t off_cand = off_cnt + al((size_t)strips * 2 * TILE_M * 4);
+  const size_t total = off_cand + (size_t)strips * 2 * TILE_M * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* sc = (char*)h->scratch;
   void* planes = sc + off_q;
   p.cand_cnt = (int*)(sc + off_cnt);
   p.cand = (u64*)(sc + off_cand);
-  p.q_lo = reinterpret_cast<const uint4*>((const char*)planes + (size_t)p.q_pad * MMF_DIM * 2);
+  p.g_tau = (u32*)(sc + off_tau);
+  p.q_plane0 = reinterpret_cast<const uint4*>(planes);
 
-  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes);
+  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau);
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;

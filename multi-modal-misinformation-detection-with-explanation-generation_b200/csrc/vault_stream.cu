@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
   constexpr int C = 32 * KPL;          // candidate capacity per query
   constexpr int LIMIT = C - 64;        // compaction trigger (two 32-row intervals of slack)
   constexpr int NLD = BF16 ? 2 : 4;    // 128-bit loads per lane per row
-  __shared__ u64 buf[QC][C];
+  constexpr int POOL = (QC * C > 2048) ? QC * C : 2048;   // candidate buffers, later the merge's staging area
+  __shared__ u64 pool[POOL];
+  u64 (*buf)[C] = reinterpret_cast<u64 (*)[C]>(pool);
   __shared__ int cnt[QC];
   __shared__ volatile float tau[QC];
   __shared__ u32 tau_key[QC];
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
     src.k_in = k;
     src.list_stride = (long long)p.n_queries * k;
     src.count_stride = p.n_queries;
-    block_select_topk(src, k, sel, p.out_scores ? p.out_scores + qg * k : nullptr,
+    block_select_topk(src, k, sel, pool, POOL, (u64)(*reinterpret_cast<volatile u32*>(p.g_tau + qg)) << 32, p.out_scores ? p.out_scores + qg * k : nullptr,
                       p.out_rows ? p.out_rows + qg * k : nullptr, p.out_packed ? p.out_packed + qg * k : nullptr,
                       p.out_disc ? p.out_disc + qg : nullptr, p.threshold);
   }
@@ -222,6 +224,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const u64* __restrict__
                                                          float* out_scores, long long* out_rows, u64* out_packed,
                                                          float* out_disc) {
   __shared__ SelectSmem sel;
+  __shared__ u64 staging[4096];
   const long long qg = blockIdx.x;
   CandidateLists src;
   src.lists = packed + qg * k_in;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const u64* __restrict__
   src.k_in = k_in;
   src.list_stride = n_queries * k_in;
   src.count_stride = 0;
-  block_select_topk(src, top_k, sel, out_scores ? out_scores + qg * top_k : nullptr,
+  block_select_topk(src, top_k, sel, staging, 4096, 0ull, out_scores ? out_scores + qg * top_k : nullptr,
                     out_rows ? out_rows + qg * top_k : nullptr, out_packed ? out_packed + qg * top_k : nullptr,
                     out_disc ? out_disc + qg : nullptr, threshold);
 }

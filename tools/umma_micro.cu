@@ -1,0 +1,149 @@
+// Microbenchmark: cycles per tcgen05.mma (cta_group::1, kind::f16, M=128, K=16) issued back to back by
+// one thread per SM, for N in {64,128,256}, A from shared memory (SS) or tensor memory (TS), and for
+// 1 or 2 alternating accumulators.  Operands are zeros; only timing matters.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/umma_micro tools/umma_micro.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+typedef unsigned long long u64; typedef unsigned int u32;
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ u64 desc(u32 saddr) {
+  return (u64)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__host__ __device__ constexpr u32 idesc(u32 fmt, u32 m, u32 n) { return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24); }
+__device__ __forceinline__ void mma_ss(u32 d, u64 a, u64 b, u32 id, u32 acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_ts(u32 d, u32 a, u64 b, u32 id, u32 acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(b), "r"(id), "r"(acc) : "memory");
+}
+template <int N, bool TS, int NACC>
+__global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ u64 bar; __shared__ u32 slot;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((u32*)smem)[i] = 0;
+  if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;"); }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads(); asm volatile("tcgen05.fence::after_thread_sync;");
+  const u32 tm = slot;
+  if (threadIdx.x == 0) {
+    const u64 a = desc(smem_u32(smem)), b = desc(smem_u32(smem + 16384));
+    constexpr u32 ID = idesc(1, 128, N);
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const u32 d = tm + ((NACC == 2 && (i & 1)) ? 256 : 0);
+        if (TS) mma_ts(d, tm + 256 + (NACC == 2 ? 128 : 0) + kk * 8, b + 2 * kk, ID, 1);   // A columns (garbage data)
+        else mma_ss(d, a + 2 * kk, b + 2 * kk, ID, 1);
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads();
+  if (threadIdx.x < 32) { asm volatile("tcgen05.fence::after_thread_sync;"); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm)); }
+}
+// knobs: COMMIT = tcgen05.commit after every 4 MMAs; STAGES = cycle B over that many 16 KB tiles;
+// SPIN = number of extra warps spinning on an mbarrier; RANDOM = non-zero operand data
+template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM>
+__global__ void __launch_bounds__(32 + 32 * SPIN + 32, 1) k2(int iters, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ u64 bar, spin_bar, sink_bar; __shared__ u32 slot;
+  const int nwords = (16384 + STAGES * 16384) / 4;
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+    u32 h = (i * 2654435761u) ^ (blockIdx.x * 40503u);
+    // two bf16 values in [-1,1): sign/exponent chosen so they are normal numbers
+    ((u32*)smem)[i] = RANDOM ? (((h & 0x807F807Fu) | 0x3F003F00u)) : 0u;
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&spin_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1000000;" ::"r"(smem_u32(&sink_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads(); asm volatile("tcgen05.fence::after_thread_sync;");
+  const u32 tm = slot;
+  if (threadIdx.x == 0) {
+    const u64 a = desc(smem_u32(smem));
+    constexpr u32 ID = idesc(1, 128, 128);
+    long long t0 = clock64();
+    int st = 0;
+    for (int i = 0; i < iters; ++i) {
+      const u64 b = desc(smem_u32(smem + 16384 + st * 16384));
+      st = (st + 1 == STAGES) ? 0 : st + 1;
+      const u32 d = tm + ((i >> 3) & 1) * 128;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (TS) mma_ts(d, tm + 256 + (i & 7) * 32 + kk * 8, b + 2 * kk, ID, 1);
+        else mma_ss(d, a + 2 * kk, b + 2 * kk, ID, 1);
+      }
+      if (COMMIT) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&sink_bar)) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D2;\n\tbra W2;\n\tD2:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
+    long long t1 = clock64();
+    if (blockIdx.x == 0) out[0] = t1 - t0;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&spin_bar)) : "memory");
+  } else if (threadIdx.x >= 64) {
+    asm volatile("{\n\t.reg .pred p;\n\tW3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D3;\n\tbra W3;\n\tD3:\n\t}" ::"r"(smem_u32(&spin_bar)) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads();
+  if (threadIdx.x < 32) { asm volatile("tcgen05.fence::after_thread_sync;"); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm)); }
+}
+template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM> void run2(const char* name) {
+  long long* out; cudaMalloc(&out, 8);
+  const int smem = 16384 + STAGES * 16384 + 1024, iters = 4000;
+  cudaFuncSetAttribute(k2<TS, COMMIT, STAGES, SPIN, RANDOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int r = 0; r < 2; ++r) { k2<TS, COMMIT, STAGES, SPIN, RANDOM><<<148, 64 + 32 * SPIN, smem>>>(iters, out); cudaDeviceSynchronize(); }
+  cudaError_t e = cudaGetLastError();
+  long long c = 0; cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
+  printf("%-60s %7.1f clk / MMA  %s\n", name, (double)c / (iters * 4.0), e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(out);
+}
+template <int N, bool TS, int NACC> void run(const char* name, int grid) {
+  long long* out; cudaMalloc(&out, 8);
+  const int smem = 16384 + 32768 + 1024, iters = 2000;
+  cudaFuncSetAttribute(k<N, TS, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<N, TS, NACC><<<grid, 128, smem>>>(iters, out); cudaDeviceSynchronize();
+  k<N, TS, NACC><<<grid, 128, smem>>>(iters, out);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0; cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
+  printf("%-28s grid %3d: %7.1f clk / MMA   (floor %d)  %s\n", name, grid, (double)c / (iters * 4.0), N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  cudaFree(out);
+}
+int main() {
+  for (int grid : {1, 148}) {
+    run<64, false, 1>("SS N=64  1 acc", grid);  run<128, false, 1>("SS N=128 1 acc", grid); run<256, false, 1>("SS N=256 1 acc", grid);
+    run<128, false, 2>("SS N=128 2 acc alternating", grid);
+    run<64, true, 1>("TS N=64  1 acc", grid);   run<128, true, 1>("TS N=128 1 acc", grid);  run<256, true, 1>("TS N=256 1 acc", grid);
+    run<128, true, 2>("TS N=128 2 acc alternating", grid);
+  }
+  printf("--- N=128, grid 148, knobs ---\n");
+  run2<false, false, 1, 0, false>("SS base (zeros, 1 B tile, no commit, no spinners)");
+  run2<false, true, 1, 0, false>("SS + commit per 4 MMAs");
+  run2<false, false, 12, 0, false>("SS + B cycling over 12 tiles");
+  run2<false, false, 1, 8, false>("SS + 8 spinning warps");
+  run2<false, false, 1, 0, true>("SS + random data");
+  run2<false, true, 12, 8, true>("SS + all");
+  run2<true, false, 1, 0, false>("TS base");
+  run2<true, true, 1, 0, false>("TS + commit per 4 MMAs");
+  run2<true, false, 12, 0, false>("TS + B cycling over 12 tiles");
+  run2<true, false, 1, 8, false>("TS + 8 spinning warps");
+  run2<true, false, 1, 0, true>("TS + random data");
+  run2<true, true, 12, 8, true>("TS + all");
+  return 0;
+}
