@@ -45,11 +45,13 @@ constexpr int KBLK = 64;             // elements per k-block: 128 B rows, one 12
 constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB: [128 rows][64 elements]
 constexpr int TILE_N = 128;          // vault rows per tile (UMMA N); 2 accumulator buffers = 256 TMEM columns
 constexpr int Q_RESIDENT_BYTES = (MMF_DIM / KBLK) * TILE_BYTES;   // 128 KB
-// smem: bf16 mode = 12 stages x 16 KB; fp32-exact = resident ql (128 KB) + 3 stages x (vh + vl = 32 KB)
-__host__ __device__ constexpr int mma_stages(bool split) { return split ? 3 : 12; }
-__host__ __device__ constexpr int stage_bytes(bool split) { return split ? 2 * TILE_BYTES : TILE_BYTES; }
-__host__ __device__ constexpr int mma_smem_bytes(bool split) {
-  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split) * stage_bytes(split);
+// A stage holds this CTA's share of one 128-row x 64-element vault k-block: 128/CG rows of 128 B per
+// plane (CG = CTAs per MMA: with cta_group::2 each CTA of the pair stores HALF of the B tile).
+// smem: bf16 = 12 x 16 KB (CG 1) / 16 x 8 KB (CG 2); fp32-exact = resident ql (128 KB) + 3 x 32 KB / 6 x 16 KB
+__host__ __device__ constexpr int stage_bytes(bool split, int cg) { return (split ? 2 : 1) * TILE_BYTES / cg; }
+__host__ __device__ constexpr int mma_stages(bool split, int cg) { return split ? 3 * cg : (cg == 1 ? 12 : 16); }
+__host__ __device__ constexpr int mma_smem_bytes(bool split, int cg) {
+  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg) * stage_bytes(split, cg);
 }
 constexpr int NUM_KBLK = MMF_DIM / KBLK;     // 8
 constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter: a lone warp per scheduler cannot hide its own latency
@@ -63,10 +65,10 @@ struct MmaParams {
   long long n_rows;        // vault rows in this shard
   u32 row_base;            // global id of row 0
   int top_k;
-  int q_tiles, v_tiles;
-  long long units;         // q_tiles * v_tiles
-  u64* cand;               // [strip][2 column halves][TILE_M][C]
-  int* cand_cnt;           // [strip][2][TILE_M]
+  int q_tiles, v_tiles;    // q_tiles is padded to a multiple of CG
+  long long units;         // (q_tiles / CG) * v_tiles: one unit = CG query tiles x one vault tile
+  u64* cand;               // [strip][2 column halves][CG][TILE_M][C]
+  int* cand_cnt;           // [strip][2][CG][TILE_M]
   u32* g_tau;              // [q_pad] best known lower bound of each query's k-th best (score key), shared grid-wide
   float inv_scale;         // accumulator -> score
   int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
@@ -120,6 +122,49 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- thread-block pair (cta_group::2) ------------------------------------------------------
+__device__ __forceinline__ u32 cluster_ctarank() { u32 r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ u32 mapa(u32 local, u32 rank) {
+  u32 r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(u32 cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier that may live in the PEER CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* map, u32 bar_cluster_addr, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(void* dst, const CUtensorMap* map, u32 bar_cluster_addr, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// 2-CTA UMMA (M = 256: 128 rows from each CTA's A operand, each CTA holds half of B), issued by the leader
+__device__ __forceinline__ void umma_f16_cg2(u32 tmem_d, u64 desc_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_cg2(u32 tmem_d, u32 tmem_a, u64 desc_b, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// commit of the leader's MMAs, arriving on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_cg2(u64* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((unsigned short)3) : "memory");
 }
 
 // one lane of a converged warp (always the same one, so tcgen05.commit sees that lane's MMAs)
@@ -227,14 +272,20 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 }
 
 // ---- the search kernel ---------------------------------------------------------------------
-template <bool SPLIT, int KPL>
+// CG = 1: one CTA per MMA (M = 128).  CG = 2: a thread-block PAIR per MMA (tcgen05 cta_group::2,
+// M = 256 = two query tiles, one per CTA); each CTA streams and stores only half of every vault
+// tile, which halves the shared-memory traffic per flop -- measured, shared-memory bandwidth (TMA
+// fill + tensor-core operand fetch = 128 B/clk) is what bounds the CG = 1 kernel.
+template <bool SPLIT, int KPL, int CG>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
-  constexpr int STAGES = mma_stages(SPLIT);
-  constexpr int STAGE_BYTES = stage_bytes(SPLIT);
+  constexpr int STAGES = mma_stages(SPLIT, CG);
+  constexpr int STAGE_BYTES = stage_bytes(SPLIT, CG);
+  constexpr int PLANE_BYTES = TILE_BYTES / CG;       // one plane of this CTA's share of a B k-block
+  constexpr int B_ROWS = TILE_N / CG;
   constexpr int C = 32 * KPL;
-  constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M, TILE_N);
+  constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M * CG, TILE_N);
   constexpr u32 QA_COL = 2 * TILE_N;                 // TMEM columns [256,512): plane 0 of the query tile
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -249,77 +300,101 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   u64* q_empty = q_full + 1;          // MMA -> producer: every MMA of the previous strip retired
   u64* qa_full = q_empty + 1;         // epilogue -> MMA: plane 0 written to tensor memory
   u32* tmem_slot = reinterpret_cast<u32*>(qa_full + 1);
+  // With CG = 2 the MMA issuer lives in the leader CTA (rank 0): full / tmem_empty / q_full / qa_full
+  // are used in the leader only (the peer signals them remotely); empty / tmem_full / q_empty exist
+  // in both CTAs and receive the leader's multicast commits.
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long u0 = (long long)blockIdx.x * p.units / gridDim.x;
-  const long long u1 = (long long)(blockIdx.x + 1) * p.units / gridDim.x;
+  const u32 rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x / CG, n_pairs = gridDim.x / CG;
+  const long long u0 = (long long)pair * p.units / n_pairs;
+  const long long u1 = (long long)(pair + 1) * p.units / n_pairs;
 
   if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, EPI_WARPS * CG); }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
-    mbar_init(qa_full, EPI_WARPS);
+    mbar_init(qa_full, EPI_WARPS * CG);
     fence_barrier_init();
   }
   if (warp == MMA_WARP) {   // the whole tensor memory: accumulators + query operand
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const u32 tmem_base = *tmem_slot;
 
   if (warp == PRODUCER_WARP) {
-    // ===== TMA producer =====
+    // ===== TMA producer (both CTAs of a pair: each loads its own share) =====
     if (lane == 0) {
       u32 it = 0, strip = 0;
-      int cur_qt = -1;
-      int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+      int cur_tp = -1;
+      int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);      // tp: index of the group of CG query tiles
+      const u32 q_full_l = (CG == 2) ? mapa(smem_u32(q_full), 0) : smem_u32(q_full);
       for (long long u = u0; u < u1; ++u, ++vt) {
-        if (vt == p.v_tiles) { vt = 0; ++qt; }
-        if (SPLIT && qt != cur_qt) {                  // new strip: (re)load the resident ql tile (plane 1)
-          cur_qt = qt;
+        if (vt == p.v_tiles) { vt = 0; ++tp; }
+        if (SPLIT && tp != cur_tp) {                  // new strip: (re)load this CTA's resident ql tile (plane 1)
+          cur_tp = tp;
           mbar_wait(q_empty, (strip & 1) ^ 1);
-          mbar_expect_tx(q_full, Q_RESIDENT_BYTES);
-          for (int kb = 0; kb < NUM_KBLK; ++kb)
-            tma_load_2d(q_smem + kb * TILE_BYTES, &tm_a, q_full, kb * KBLK, p.q_pad + qt * TILE_M);
+          if (leader) mbar_expect_tx(q_full, Q_RESIDENT_BYTES * CG);
+          const int qrow = p.q_pad + (tp * CG + (int)rank) * TILE_M;
+          for (int kb = 0; kb < NUM_KBLK; ++kb) {
+            if (CG == 2) tma_load_2d_cg2(q_smem + kb * TILE_BYTES, &tm_a, q_full_l, kb * KBLK, qrow);
+            else tma_load_2d(q_smem + kb * TILE_BYTES, &tm_a, q_full, kb * KBLK, qrow);
+          }
           ++strip;
         }
+        const int brow = vt * TILE_N + (int)rank * B_ROWS;
         for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
           unsigned char* st = stage_smem + s * STAGE_BYTES;
-          if (p.debug & 2) { mbar_arrive(full_bar + s); continue; }
-          mbar_expect_tx(full_bar + s, STAGE_BYTES);
-          if (SPLIT) {
-            tma_load_3d(st, &tm_b, full_bar + s, kb * KBLK, 0, vt * TILE_N);
-            tma_load_3d(st + TILE_BYTES, &tm_b, full_bar + s, kb * KBLK, 1, vt * TILE_N);
+          if (p.debug & 2) { if (leader) mbar_arrive(full_bar + s); continue; }
+          if (leader) mbar_expect_tx(full_bar + s, STAGE_BYTES * CG);
+          if (CG == 2) {
+            const u32 fb = mapa(smem_u32(full_bar + s), 0);
+            if (SPLIT) {
+              tma_load_3d_cg2(st, &tm_b, fb, kb * KBLK, 0, brow);
+              tma_load_3d_cg2(st + PLANE_BYTES, &tm_b, fb, kb * KBLK, 1, brow);
+            } else {
+              tma_load_2d_cg2(st, &tm_b, fb, kb * KBLK, brow);
+            }
+          } else if (SPLIT) {
+            tma_load_3d(st, &tm_b, full_bar + s, kb * KBLK, 0, brow);
+            tma_load_3d(st + PLANE_BYTES, &tm_b, full_bar + s, kb * KBLK, 1, brow);
           } else {
-            tma_load_2d(st, &tm_b, full_bar + s, kb * KBLK, vt * TILE_N);
+            tma_load_2d(st, &tm_b, full_bar + s, kb * KBLK, brow);
           }
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (leader CTA only) =====
     // The WHOLE warp runs the loop so that addresses and descriptors are computed once, in the
     // uniform datapath; only the tcgen05 instructions themselves are issued by the elected lane.
-    {
+    if (leader) {
       u32 it = 0, tile = 0, strip = 0;
-      int cur_qt = -1;
+      int cur_tp = -1;
       const u32 q_addr = smem_u32(q_smem);
       const u32 st_addr = smem_u32(stage_smem);
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
       const long long t_begin = clock64();
-      int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+      int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
       for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
-        if (vt == p.v_tiles) { vt = 0; ++qt; }
-        if (qt != cur_qt) {
-          cur_qt = qt;
+        if (vt == p.v_tiles) { vt = 0; ++tp; }
+        if (tp != cur_tp) {
+          cur_tp = tp;
           if (SPLIT) mbar_wait(q_full, strip & 1);
           mbar_wait(qa_full, strip & 1);
           ++strip;
@@ -338,20 +413,28 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           const u32 qa = tmem_base + QA_COL + kb * (KBLK / 2);     // 2 elements per column
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k)        // qh.vh  (bf16 mode: q.v); A from tensor memory
-              umma_f16_ts(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
+            for (int k = 0; k < KBLK / 16; ++k) {      // qh.vh  (bf16 mode: q.v); A from tensor memory
+              if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
+              else umma_f16_ts(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
+            }
             if (SPLIT) {
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k)      // qh.vl
-                umma_f16_ts(d_tmem, qa + k * 8, vb + (TILE_BYTES >> 4) + 2 * k, IDESC, 1);
+              for (int k = 0; k < KBLK / 16; ++k) {    // qh.vl
+                if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
+                else umma_f16_ts(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
+              }
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k)      // ql.vh, ql from shared memory (+2 = 32 B = 16 elements)
-                umma_f16(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+              for (int k = 0; k < KBLK / 16; ++k) {    // ql.vh, ql from shared memory (+2 = 32 B = 16 elements)
+                if (CG == 2) umma_f16_cg2(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+                else umma_f16(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+              }
             }
-            umma_commit(empty_bar + s);               // smem slot free once these MMAs retire
+            if (CG == 2) umma_commit_cg2(empty_bar + s); else umma_commit(empty_bar + s);   // smem slot free once these MMAs retire
             if (kb == NUM_KBLK - 1) {
-              umma_commit(tmem_full + acc);           // accumulator complete -> epilogue
-              if (SPLIT && (u + 1 == u1 || vt + 1 == p.v_tiles)) umma_commit(q_empty);   // strip done
+              if (CG == 2) umma_commit_cg2(tmem_full + acc); else umma_commit(tmem_full + acc);   // accumulator complete
+              if (SPLIT && (u + 1 == u1 || vt + 1 == p.v_tiles)) {                                 // strip done
+                if (CG == 2) umma_commit_cg2(q_empty); else umma_commit(q_empty);
+              }
             }
           }
           __syncwarp();
@@ -373,25 +456,28 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const int half = warp >> 2;
     const int m = quarter * 32 + lane;
     const u32 lane_base = tmem_base + ((u32)(quarter * 32) << 16);
+    const u32 tmem_empty_l = (CG == 2) ? mapa(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
+    const u32 qa_full_l = (CG == 2) ? mapa(smem_u32(qa_full), 0) : smem_u32(qa_full);
     const int k = p.top_k;
     const float acc_scale = 1.0f / p.inv_scale;
     float tau_acc = -INFINITY;                        // threshold in accumulator units
     int cnt = 0;
-    int cur_qt = -1;
+    int cur_tp = -1;
     u64* buf = nullptr;
     int* cnt_out = nullptr;
     u32* g_tau = nullptr;
     bool valid_q = false;
     u32 tile = 0;
-    int qt = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
+    int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
     for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
-      if (vt == p.v_tiles) { vt = 0; ++qt; }
-      if (qt != cur_qt) {                             // new strip: flush the old one, reset state
-        if (cur_qt >= 0) *cnt_out = cnt;
-        cur_qt = qt;
+      if (vt == p.v_tiles) { vt = 0; ++tp; }
+      if (tp != cur_tp) {                             // new strip: flush the old one, reset state
+        if (cur_tp >= 0) *cnt_out = cnt;
+        cur_tp = tp;
         cnt = 0;
         tau_acc = -INFINITY;
-        const long long list = ((long long)(blockIdx.x + qt) * 2 + half) * TILE_M + m;
+        const int qt = tp * CG + (int)rank;           // this CTA's query tile
+        const long long list = (((long long)(pair + tp) * 2 + half) * CG + rank) * TILE_M + m;
         buf = p.cand + list * C;
         cnt_out = p.cand_cnt + list;
         g_tau = p.g_tau + qt * TILE_M + m;
@@ -414,7 +500,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           tmem_wait_st();
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(qa_full);
+          if (lane == 0) { if (CG == 2) mbar_arrive_cluster(qa_full_l); else mbar_arrive(qa_full); }
         }
       }
       // a tighter bound found by any other block / warp for this query (valid for every list of it);
@@ -431,14 +517,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 #pragma unroll 1
       for (int c = half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += 2) {
         u32 v[32];
-        if (p.debug & 16) {                            // triage: no TMEM read
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0xff800000u;
-        } else {
-          tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
-          tmem_wait_ld();
-        }
-        if (p.debug & 32) continue;                    // triage: TMEM read only
+        tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
+        tmem_wait_ld();
         // fast path (almost always): chunk maximum below the threshold.  A max tree keeps the
         // dependent chain short.  (fmaxf drops a NaN next to a number; vaults with NaN rows never
         // reach this kernel, see mmf_mma_supported.)
@@ -448,31 +528,24 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        // slow path, warp-uniform and deliberately SMALL in code: the MMA warp's issue loop is latency
-        // critical and a large unrolled epilogue evicts it from the instruction cache (measured: +300
-        // clk per k-block).  Re-read the chunk 8 columns at a time and append the survivors.
-        if (__any_sync(FULL, !(m8 < tau_acc) && valid_q)) {
-#pragma unroll 1
-          for (int g = 0; g < 4; ++g) {
-            u32 w[8];
-            tmem_ld8(lane_base + acc * TILE_N + c * 32 + g * 8, w);
-            tmem_wait_ld();
-            if (valid_q) {
+        if (!(m8 < tau_acc) && valid_q) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float a = __uint_as_float(w[e]);
-                const int col = c * 32 + g * 8 + e;
+          for (int i = 0; i < 8; ++i) {
+            if (!(mx[i] < tau_acc)) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = __uint_as_float(v[4 * i + e]);
+                const int col = c * 32 + 4 * i + e;
                 if (!(a < tau_acc) && (!partial || col < n_cols)) buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
               }
             }
           }
         }
       }
-      // hand the accumulator back FIRST: compaction below then overlaps the next tile's MMAs instead
-      // of stalling them (the slowest of the 8 warps gates tmem_empty)
+      // hand the accumulator back FIRST: compaction below then overlaps the next tile's MMAs
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + acc);
+      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
       constexpr int ROOM = 32 * (TILE_N / 32 / 2);
       static_assert(C - ROOM >= 32, "candidate capacity too small for a tile");
@@ -493,20 +566,21 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         __syncwarp();
       }
     }
-    if (cur_qt >= 0) *cnt_out = cnt;
+    if (cur_tp >= 0) *cnt_out = cnt;
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's smem / TMEM must outlive the leader's MMAs
   if (warp == MMA_WARP) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
 // One block per query: gather the strips that cover its query tile, select + sort the top-k.
-template <int KPL>
-__global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int grid_main, double threshold,
+template <int KPL, int CG>
+__global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
                                                         float* out_scores, long long* out_rows, u64* out_packed,
                                                         float* out_disc) {
   constexpr int C = 32 * KPL;
@@ -515,11 +589,12 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int g
   __shared__ int s_first, s_count;
   const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
+  const int tp = qt / CG, r = qt % CG;
   if (threadIdx.x == 0) {
     int first = -1, count = 0;
-    const long long lo = (long long)qt * p.v_tiles, hi = lo + p.v_tiles;
-    for (int c = 0; c < grid_main; ++c) {
-      const long long a = (long long)c * p.units / grid_main, b = (long long)(c + 1) * p.units / grid_main;
+    const long long lo = (long long)tp * p.v_tiles, hi = lo + p.v_tiles;
+    for (int c = 0; c < n_pairs; ++c) {
+      const long long a = (long long)c * p.units / n_pairs, b = (long long)(c + 1) * p.units / n_pairs;
       if (a < hi && b > lo && b > a) {
         if (first < 0) first = c;
         ++count;
@@ -529,14 +604,17 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int g
     s_count = count;
   }
   __syncthreads();
+  // lists of this query: [strip = pair + tp][half][r][m][C], contiguous in (strip, half)
   CandidateLists src;
-  src.lists = p.cand + ((long long)(s_first + qt) * 2 * TILE_M + m) * C;     // [strip][half][m][C]
-  src.counts = p.cand_cnt + (long long)(s_first + qt) * 2 * TILE_M + m;
+  const long long base = (((long long)(s_first + tp) * 2) * CG + r) * TILE_M + m;
+  src.lists = p.cand + base * C;
+  src.counts = p.cand_cnt + base;
   src.n_lists = 2 * s_count;
   src.k_in = C;
-  src.list_stride = (long long)TILE_M * C;
-  src.count_stride = TILE_M;
-  block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+  src.list_stride = (long long)CG * TILE_M * C;
+  src.count_stride = CG * TILE_M;
+  block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32,
+                    out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
                     threshold);
@@ -553,9 +631,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct MmaState {
   EncodeTiledFn encode = nullptr;
-  CUtensorMap tm_vault;
+  CUtensorMap tm_vault[2];        // [0]: box of 128 rows (CG = 1), [1]: box of 64 rows (CG = 2)
   bool vault_map_ok = false;
-  bool attrs_set = false;
 };
 
 static MmaState* state_of(mmf_handle* h) {
@@ -587,18 +664,22 @@ int mmf_mma_vault_changed(mmf_handle* h) {
   if (!s) return MMF_OK;
   s->vault_map_ok = false;
   if (!s->encode || !h->vault || h->vault_rows <= 0) return MMF_OK;
-  if (h->vault_mode == MMF_VAULT_BF16) {
-    const cuuint64_t dims[2] = {MMF_DIM, (cuuint64_t)h->vault_rows};
-    const cuuint64_t strides[1] = {MMF_DIM * 2};
-    const cuuint32_t box[2] = {KBLK, TILE_N};
-    s->vault_map_ok = encode_map(s, &s->tm_vault, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->vault, dims, strides, box);
-  } else {
-    // [row][plane][512] fp16 viewed as (k, plane, row)
-    const cuuint64_t dims[3] = {MMF_DIM, 2, (cuuint64_t)h->vault_rows};
-    const cuuint64_t strides[2] = {MMF_DIM * 2, MMF_DIM * 4};
-    const cuuint32_t box[3] = {KBLK, 1, TILE_N};
-    s->vault_map_ok = encode_map(s, &s->tm_vault, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->vault, dims, strides, box);
+  bool ok = true;
+  for (int cg = 1; cg <= 2; ++cg) {
+    if (h->vault_mode == MMF_VAULT_BF16) {
+      const cuuint64_t dims[2] = {MMF_DIM, (cuuint64_t)h->vault_rows};
+      const cuuint64_t strides[1] = {MMF_DIM * 2};
+      const cuuint32_t box[2] = {KBLK, (cuuint32_t)(TILE_N / cg)};
+      ok = ok && encode_map(s, &s->tm_vault[cg - 1], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, h->vault, dims, strides, box);
+    } else {
+      // [row][plane][512] fp16 viewed as (k, plane, row)
+      const cuuint64_t dims[3] = {MMF_DIM, 2, (cuuint64_t)h->vault_rows};
+      const cuuint64_t strides[2] = {MMF_DIM * 2, MMF_DIM * 4};
+      const cuuint32_t box[3] = {KBLK, 1, (cuuint32_t)(TILE_N / cg)};
+      ok = ok && encode_map(s, &s->tm_vault[cg - 1], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, h->vault, dims, strides, box);
+    }
   }
+  s->vault_map_ok = ok;
   return MMF_OK;
 }
 
@@ -614,16 +695,29 @@ void mmf_mma_destroy(mmf_handle* h) {
   h->mma_state = nullptr;
 }
 
-template <bool SPLIT, int KPL>
-static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int grid, double threshold,
-                      float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st) {
-  const int smem = mma_smem_bytes(SPLIT) + 256 + 1024;
-  auto kern = vault_mma_topk_kernel<SPLIT, KPL>;
+template <bool SPLIT, int KPL, int CG>
+static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
+                      double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
+                      cudaStream_t st) {
+  const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
+  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, MMA_THREADS, smem, st>>>(tm_q, s->tm_vault, p);
-  MMF_LAUNCH_OK(h);
-  mma_merge_kernel<KPL><<<p.n_queries, 256, 0, st>>>(p, grid, threshold, out_scores, (long long*)out_rows,
-                                                      (u64*)out_packed, out_disc);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(n_pairs * CG));
+  cfg.blockDim = dim3(MMA_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
+  h->launches++;
+  mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                          (u64*)out_packed, out_disc);
   MMF_LAUNCH_OK(h);
   return MMF_OK;
 }
@@ -639,26 +733,31 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const int C = 32 * kpl;
 
   MmaParams p;
+  { const char* e = getenv("MMF_MMA_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  // a thread-block pair per MMA as soon as there are two query tiles to pair up
+  int cg = n_queries > TILE_M ? 2 : 1;
+  { const char* e = getenv("MMF_MMA_CG"); if (e && (atoi(e) == 1 || atoi(e) == 2)) cg = atoi(e); }
   p.n_queries = (int)n_queries;
   p.q_tiles = (int)((n_queries + TILE_M - 1) / TILE_M);
+  p.q_tiles = (p.q_tiles + cg - 1) / cg * cg;
   p.q_pad = p.q_tiles * TILE_M;
   p.n_rows = h->vault_rows;
   p.row_base = (u32)h->vault_row_offset;
   p.top_k = top_k;
   p.v_tiles = (int)((h->vault_rows + TILE_N - 1) / TILE_N);
-  p.units = (long long)p.q_tiles * p.v_tiles;
-  { const char* e = getenv("MMF_MMA_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.units = (long long)(p.q_tiles / cg) * p.v_tiles;
   p.inv_scale = split ? (MMF_SPLIT_INV_SCALE * MMF_SPLIT_INV_SCALE) : 1.0f;
-  const int grid = (int)std::min<long long>(h->sm_count, p.units);
-  const long long strips = (long long)grid + p.q_tiles;
+  const int n_pairs = (int)std::min<long long>(h->sm_count / cg, p.units);
+  const long long strips = (long long)n_pairs + p.q_tiles / cg;
+  const long long lists = strips * 2 * cg * TILE_M;
 
-  // scratch: [64 KB counters (stream kernel) | query planes | cand_cnt | cand]
+  // scratch: [64 KB counters (stream kernel) | query planes | g_tau | cand_cnt | cand]
   auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   const size_t off_q = 65536;
   const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
   const size_t off_cnt = off_tau + al((size_t)p.q_pad * 4);
-  const size_t off_cand = off_cnt + al((size_t)strips * 2 * TILE_M * 4);
-  const size_t total = off_cand + (size_t)strips * 2 * TILE_M * C * 8;
+  const size_t off_cand = off_cnt + al((size_t)lists * 4);
+  const size_t total = off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* sc = (char*)h->scratch;
@@ -679,8 +778,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                   strides, box))
     return mmf_set_error(h, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query operand");
 
-#define MMF_MMA_CASE(SPLIT_, KPL_)                                                                                  \
-  return launch_mma<SPLIT_, KPL_>(h, s, tm_q, p, grid, threshold, out_scores, out_rows, out_packed, out_disc, st)
+#define MMF_MMA_CASE(SPLIT_, KPL_)                                                                             \
+  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
+                                               out_disc, st)                                                   \
+                 : launch_mma<SPLIT_, KPL_, 1>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
+                                               out_disc, st)
   if (split) {
     if (kpl == 4) MMF_MMA_CASE(true, 4);
     if (kpl == 8) MMF_MMA_CASE(true, 8);

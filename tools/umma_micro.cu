@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(128, 1) k(int iters, long long* out) {
 }
 // knobs: COMMIT = tcgen05.commit after every 4 MMAs; STAGES = cycle B over that many 16 KB tiles;
 // SPIN = number of extra warps spinning on an mbarrier; RANDOM = non-zero operand data
-template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM>
+template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM, int BUSY = 0>
 __global__ void __launch_bounds__(32 + 32 * SPIN + 32, 1) k2(int iters, long long* out) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -98,17 +98,33 @@ __global__ void __launch_bounds__(32 + 32 * SPIN + 32, 1) k2(int iters, long lon
     long long t1 = clock64();
     if (blockIdx.x == 0) out[0] = t1 - t0;
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&spin_bar)) : "memory");
+  } else if (threadIdx.x >= 64 && BUSY) {
+    // ALU-busy helper warps (BUSY=1: fmax/compare chains like the epilogue filter; BUSY=2: also TMEM reads)
+    float a = threadIdx.x, b = 1.0f, c = 0.5f;
+    u32 done = 0;
+    while (!done) {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) { a = fmaxf(a * 1.0001f, b); b = fmaxf(b + c, a * 0.5f); c = fmaf(c, 0.999f, 1e-3f); }
+      if (BUSY == 2) {
+        u32 v0, v1, v2, v3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(tm + (((threadIdx.x >> 5) & 3) * 32 << 16)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        a += __uint_as_float(v0 ^ v1 ^ v2 ^ v3) * 0.f;
+      }
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(&spin_bar)) : "memory");
+    }
+    if (a + b + c == 12345.678f) out[1] = 1;
   } else if (threadIdx.x >= 64) {
     asm volatile("{\n\t.reg .pred p;\n\tW3:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D3;\n\tbra W3;\n\tD3:\n\t}" ::"r"(smem_u32(&spin_bar)) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;"); __syncthreads();
   if (threadIdx.x < 32) { asm volatile("tcgen05.fence::after_thread_sync;"); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tm)); }
 }
-template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM> void run2(const char* name) {
-  long long* out; cudaMalloc(&out, 8);
+template <bool TS, bool COMMIT, int STAGES, int SPIN, bool RANDOM, int BUSY = 0> void run2(const char* name) {
+  long long* out; cudaMalloc(&out, 16);
   const int smem = 16384 + STAGES * 16384 + 1024, iters = 4000;
-  cudaFuncSetAttribute(k2<TS, COMMIT, STAGES, SPIN, RANDOM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int r = 0; r < 2; ++r) { k2<TS, COMMIT, STAGES, SPIN, RANDOM><<<148, 64 + 32 * SPIN, smem>>>(iters, out); cudaDeviceSynchronize(); }
+  cudaFuncSetAttribute(k2<TS, COMMIT, STAGES, SPIN, RANDOM, BUSY>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  for (int r = 0; r < 2; ++r) { k2<TS, COMMIT, STAGES, SPIN, RANDOM, BUSY><<<148, 64 + 32 * SPIN, smem>>>(iters, out); cudaDeviceSynchronize(); }
   cudaError_t e = cudaGetLastError();
   long long c = 0; cudaMemcpy(&c, out, 8, cudaMemcpyDeviceToHost);
   printf("%-60s %7.1f clk / MMA  %s\n", name, (double)c / (iters * 4.0), e == cudaSuccess ? "" : cudaGetErrorString(e));
@@ -145,5 +161,8 @@ int main() {
   run2<true, false, 1, 8, false>("TS + 8 spinning warps");
   run2<true, false, 1, 0, true>("TS + random data");
   run2<true, true, 12, 8, true>("TS + all");
+  run2<true, true, 12, 8, true, 1>("TS + all + 8 ALU-busy warps");
+  run2<true, true, 12, 8, true, 2>("TS + all + 8 ALU-busy warps reading TMEM");
+  run2<false, true, 12, 8, true, 1>("SS + all + 8 ALU-busy warps");
   return 0;
 }
