@@ -85,7 +85,7 @@ __device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(u64* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
   asm volatile(
@@ -134,8 +134,11 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ u32 mapa(u32 local, u32 rank) {
   u32 r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank)); return r;
 }
+// relaxed on purpose: the barriers signalled this way only order TENSOR-MEMORY accesses (done with
+// tcgen05.fence); a release here would drain this thread's outstanding global stores (candidate appends)
+// at cluster scope on every tile -- measured at ~25% of all epilogue stall samples.
 __device__ __forceinline__ void mbar_arrive_cluster(u32 cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on a barrier that may live in the PEER CTA of the pair
 __device__ __forceinline__ void tma_load_2d_cg2(void* dst, const CUtensorMap* map, u32 bar_cluster_addr, int c0, int c1) {
@@ -467,7 +470,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     int* cnt_out = nullptr;
     u32* g_tau = nullptr;
     bool valid_q = false;
-    u32 tile = 0;
+    u32 tile = 0, g_prev = 0;
     int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
     for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
       if (vt == p.v_tiles) { vt = 0; ++tp; }
@@ -475,6 +478,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         if (cur_tp >= 0) *cnt_out = cnt;
         cur_tp = tp;
         cnt = 0;
+        g_prev = 0;
         tau_acc = -INFINITY;
         const int qt = tp * CG + (int)rank;           // this CTA's query tile
         const long long list = (((long long)(pair + tp) * 2 + half) * CG + rank) * TILE_M + m;
@@ -503,13 +507,14 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(qa_full_l); else mbar_arrive(qa_full); }
         }
       }
-      // a tighter bound found by any other block / warp for this query (valid for every list of it);
-      // issued before the wait so its latency hides behind the MMAs
-      const u32 g_seen = *reinterpret_cast<volatile u32*>(g_tau);
+      // a tighter bound found by any other block / warp for this query (valid for every list of it).
+      // Software-pipelined: the value loaded during the previous tile is applied now and the next
+      // load is issued, so the L2 round trip never sits on the tile's critical path.
+      if (g_prev) tau_acc = fmaxf(tau_acc, okey_inv(g_prev) * acc_scale);
+      g_prev = *reinterpret_cast<volatile u32*>(g_tau);
       const u32 acc = tile & 1;
       mbar_wait_relaxed(tmem_full + acc, (tile >> 1) & 1);
       tcgen05_fence_after();
-      if (g_seen) tau_acc = fmaxf(tau_acc, okey_inv(g_seen) * acc_scale);
       const long long row0 = (long long)vt * TILE_N;
       const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
       const bool partial = n_cols < TILE_N;           // beyond n_cols the tile is TMA zero fill
