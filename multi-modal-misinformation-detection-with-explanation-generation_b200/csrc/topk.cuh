@@ -12,29 +12,35 @@
 
 namespace mmf {
 
-// k-th largest of the warp-distributed keys (KPL per lane, 0 = empty); bitwise descent,
-// first on the score word, then (only if several candidates tie on it) on the row word.
+// k-th largest of the warp-distributed keys (KPL per lane, 0 = empty): radix-4 descent on the score
+// word (16 rounds, the 3 candidate thresholds of a round are counted independently with ballots, so a
+// round costs one ballot latency, not three dependent reductions), then -- only if several candidates
+// tie on the score -- a bitwise descent on the row word.
+template <int KPL>
+__device__ __forceinline__ int warp_count_ge(const u64 (&key)[KPL], u32 cand) {
+  int c = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) c += __popc(__ballot_sync(FULL, (u32)(key[r] >> 32) >= cand));
+  return c;
+}
+
 template <int KPL>
 __device__ __forceinline__ u64 warp_kth_largest(const u64 (&key)[KPL], int k) {
   u32 t_hi = 0;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
-    const u32 cand = t_hi | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int r = 0; r < KPL; ++r) c += ((u32)(key[r] >> 32) >= cand);
-    c = __reduce_add_sync(FULL, c);
-    if (c >= k) t_hi = cand;
+  for (int shift = 30; shift >= 0; shift -= 2) {
+    const int c1 = warp_count_ge<KPL>(key, t_hi | (1u << shift));
+    const int c2 = warp_count_ge<KPL>(key, t_hi | (2u << shift));
+    const int c3 = warp_count_ge<KPL>(key, t_hi | (3u << shift));
+    t_hi |= (c3 >= k ? 3u : c2 >= k ? 2u : c1 >= k ? 1u : 0u) << shift;
   }
   int gt = 0, eq = 0;
 #pragma unroll
   for (int r = 0; r < KPL; ++r) {
     const u32 hi = (u32)(key[r] >> 32);
-    gt += (hi > t_hi);
-    eq += (hi == t_hi) && key[r] != 0;
+    gt += __popc(__ballot_sync(FULL, hi > t_hi));
+    eq += __popc(__ballot_sync(FULL, hi == t_hi && key[r] != 0));
   }
-  gt = __reduce_add_sync(FULL, gt);
-  eq = __reduce_add_sync(FULL, eq);
   const int need = k - gt;                 // how many of the tied candidates survive
   u32 t_lo = 0;
   if (eq > need && t_hi != 0) {            // warp-uniform
@@ -43,8 +49,7 @@ __device__ __forceinline__ u64 warp_kth_largest(const u64 (&key)[KPL], int k) {
       const u32 cand = t_lo | (1u << bit);
       int c = 0;
 #pragma unroll
-      for (int r = 0; r < KPL; ++r) c += ((u32)(key[r] >> 32) == t_hi) && ((u32)key[r] >= cand);
-      c = __reduce_add_sync(FULL, c);
+      for (int r = 0; r < KPL; ++r) c += __popc(__ballot_sync(FULL, (u32)(key[r] >> 32) == t_hi && (u32)key[r] >= cand));
       if (c >= need) t_lo = cand;
     }
   }

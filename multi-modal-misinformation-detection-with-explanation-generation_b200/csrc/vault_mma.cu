@@ -69,6 +69,7 @@ struct MmaParams {
   long long units;         // (q_tiles / CG) * v_tiles: one unit = CG query tiles x one vault tile
   u64* cand;               // [strip][2 column halves][CG][TILE_M][C]
   int* cand_cnt;           // [strip][2][CG][TILE_M]
+  u32* pool;               // [q_pad][16] bucket maxima (row % top_k) for top_k <= 16; min over buckets is a grid-wide bound
   u32* g_tau;              // [q_pad] best known lower bound of each query's k-th best (score key), shared grid-wide
   float inv_scale;         // accumulator -> score
   int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
@@ -245,11 +246,13 @@ __host__ __device__ constexpr u32 umma_idesc(u32 fmt, u32 m, u32 n) {
 // planes: bf16 (1 plane) or fp16 hi/lo of q*2^8 (2 planes, plane p at row p*q_pad + i).
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
                                                              int split, void* __restrict__ planes,
-                                                             u32* __restrict__ g_tau) {
+                                                             u32* __restrict__ g_tau, u32* __restrict__ pool,
+                                                             int top_k) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
   if (lane == 0) g_tau[w] = 0;
+  if (lane < 16) pool[w * 16 + lane] = (lane < top_k) ? 0u : 0xFFFFFFFFu;   // unused buckets never win the min
   float v[MMF_DIM / 32], ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MMF_DIM / 32; ++j) {
@@ -279,7 +282,11 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 // M = 256 = two query tiles, one per CTA); each CTA streams and stores only half of every vault
 // tile, which halves the shared-memory traffic per flop -- measured, shared-memory bandwidth (TMA
 // fill + tensor-core operand fetch = 128 B/clk) is what bounds the CG = 1 kernel.
-template <bool SPLIT, int KPL, int CG>
+// KR > 0 (top_k <= KR): every epilogue thread also keeps the KR best accumulator values of its list
+// sorted in registers, so its threshold is EXACT at all times (the k-th best of everything it has
+// seen) instead of being refreshed only when the list is compacted; far fewer candidates pass and
+// short lists never need a compaction.  KR = 0: lazy thresholds (large top_k).
+template <bool SPLIT, int KPL, int CG, int KR>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
@@ -318,7 +325,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, EPI_WARPS * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, (EPI_WARPS / 2) * CG); }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(qa_full, EPI_WARPS * CG);
@@ -393,6 +400,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u32 st_addr = smem_u32(stage_smem);
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
       const long long t_begin = clock64();
+      long long dbg_empty = 0, dbg_full = 0;
       int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
       for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
         if (vt == p.v_tiles) { vt = 0; ++tp; }
@@ -403,14 +411,18 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ++strip;
         }
         const u32 acc = tile & 1;
+        const long long t_e0 = clock64();
         if (!(p.debug & 4)) mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
         tcgen05_fence_after();
+        dbg_empty += clock64() - t_e0;
         const u32 d_tmem = tmem_base + acc * TILE_N;
 #pragma unroll 1
         for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
           const int s = it % STAGES;
+          const long long t_f0 = clock64();
           if (!(p.debug & 4)) mbar_wait(full_bar + s, (it / STAGES) & 1);
           tcgen05_fence_after();
+          dbg_full += clock64() - t_f0;
           const u64 ql = desc_hi | (u64)(((q_addr + kb * TILE_BYTES) >> 4) & 0x3FFF);
           const u64 vb = desc_hi | (u64)(((st_addr + s * STAGE_BYTES) >> 4) & 0x3FFF);
           const u32 qa = tmem_base + QA_COL + kb * (KBLK / 2);     // 2 elements per column
@@ -446,17 +458,19 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
         mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
         const long long dt = clock64() - t_begin;
-        printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block\n", tile, it,
-               dt, (double)dt / it);
+        printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block "
+               "(waiting: accumulator free %.1f, operands landed %.1f)\n", tile, it, dt, (double)dt / it,
+               (double)dbg_empty / it, (double)dbg_full / it);
       }
     }
   } else {
     // ===== epilogue: thread == query (TMEM lane), streaming top-k =====
-    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31, so two warps share each lane quarter and
-    // split the accumulator columns (32-column chunks of alternating parity).  Each thread keeps its
-    // own candidate list + threshold for its (query, column half).
+    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31.  Warps 0-3 serve accumulator buffer 0 (even
+    // tiles), warps 4-7 buffer 1 (odd tiles): each set has two tile periods to drain its tile, which
+    // absorbs the barrier hand-off latencies and compaction bursts.  Each thread keeps its own
+    // candidate list + threshold for its (query, tile parity).
     const int quarter = warp & 3;
-    const int half = warp >> 2;
+    const int half = warp >> 2;                       // tile parity == accumulator buffer served
     const int m = quarter * 32 + lane;
     const u32 lane_base = tmem_base + ((u32)(quarter * 32) << 16);
     const u32 tmem_empty_l = (CG == 2) ? mapa(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
@@ -464,18 +478,28 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const int k = p.top_k;
     const float acc_scale = 1.0f / p.inv_scale;
     float tau_acc = -INFINITY;                        // threshold in accumulator units
+    float best[KR > 0 ? KR : 1];                      // KR > 0: the KR best accumulators, descending
     int cnt = 0;
     int cur_tp = -1;
     u64* buf = nullptr;
     int* cnt_out = nullptr;
     u32* g_tau = nullptr;
+    u32* pool = nullptr;
+    uint4 pool_prev[4];
     bool valid_q = false;
     u32 tile = 0, g_prev = 0;
+    long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
+    int dbg_ncompact = 0;
     int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
     for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
       if (vt == p.v_tiles) { vt = 0; ++tp; }
       if (tp != cur_tp) {                             // new strip: flush the old one, reset state
-        if (cur_tp >= 0) *cnt_out = cnt;
+        if (cur_tp >= 0) {
+          *cnt_out = cnt;
+          // both warp sets must have drained the old strip (=> all its MMAs retired) before anyone
+          // overwrites the query operand in tensor memory
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        }
         cur_tp = tp;
         cnt = 0;
         g_prev = 0;
@@ -485,11 +509,18 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         buf = p.cand + list * C;
         cnt_out = p.cand_cnt + list;
         g_tau = p.g_tau + qt * TILE_M + m;
+        pool = p.pool + (long long)(qt * TILE_M + m) * 16;
         valid_q = (qt * TILE_M + m) < p.n_queries;
+        if (KR > 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pool_prev[i] = make_uint4(0, 0, 0, 0);
+          // slots beyond top_k hold +inf "phantoms", so best[KR-1] is always the top_k-th best
+#pragma unroll
+          for (int i = 0; i < KR; ++i) best[i] = (i < KR - k) ? INFINITY : -INFINITY;
+        }
         {
           // this thread's query row of plane 0 -> its TMEM lane, 2 elements per column (each warp of
-          // a quarter writes half of the 256 columns).  Every MMA of the previous strip has retired:
-          // its last accumulator was consumed above.
+          // a quarter writes half of the 256 columns)
           const uint4* src = p.q_plane0 + (long long)(qt * TILE_M + m) * (MMF_DIM * 2 / 16);
 #pragma unroll 1
           for (int c = half * 4; c < half * 4 + 4; ++c) {
@@ -507,20 +538,35 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(qa_full_l); else mbar_arrive(qa_full); }
         }
       }
+      if ((int)(tile & 1) != half) continue;          // the other warp set owns this tile
       // a tighter bound found by any other block / warp for this query (valid for every list of it).
       // Software-pipelined: the value loaded during the previous tile is applied now and the next
       // load is issued, so the L2 round trip never sits on the tile's critical path.
       if (g_prev) tau_acc = fmaxf(tau_acc, okey_inv(g_prev) * acc_scale);
       g_prev = *reinterpret_cast<volatile u32*>(g_tau);
+      if (KR > 0) {
+        // grid-wide bound: every bucket (row % top_k) holds the best score any block has seen among
+        // its rows -- top_k distinct rows, so the minimum over the buckets is <= the global k-th best
+        u32 mn = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mn = min(min(mn, pool_prev[i].x), min(min(pool_prev[i].y, pool_prev[i].z), pool_prev[i].w));
+        if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pool_prev[i] = __ldcv(reinterpret_cast<const uint4*>(pool) + i);
+      }
       const u32 acc = tile & 1;
-      mbar_wait_relaxed(tmem_full + acc, (tile >> 1) & 1);
+      const long long t_w0 = clock64();
+      mbar_wait(tmem_full + acc, (tile >> 1) & 1);
       tcgen05_fence_after();
+      const long long t_w1 = clock64();
+      dbg_wait += t_w1 - t_w0;
       const long long row0 = (long long)vt * TILE_N;
       const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
       const bool partial = n_cols < TILE_N;           // beyond n_cols the tile is TMA zero fill
       const u32 row_id0 = p.row_base + (u32)row0;
+      bool improved = false;
 #pragma unroll 1
-      for (int c = half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += 2) {
+      for (int c = 0; c < ((p.debug & 1) ? 0 : TILE_N / 32); ++c) {
         u32 v[32];
         tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
         tmem_wait_ld();
@@ -541,18 +587,31 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
               for (int e = 0; e < 4; ++e) {
                 const float a = __uint_as_float(v[4 * i + e]);
                 const int col = c * 32 + 4 * i + e;
-                if (!(a < tau_acc) && (!partial || col < n_cols)) buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
+                if (!(a < tau_acc) && (!partial || col < n_cols)) {
+                  buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
+                  if (KR > 0) {
+                    atomicMax(pool + (row_id0 + col) % (u32)k, okey(a * p.inv_scale));
+                    // sorted insert, branch free: new[i] = max(old[i], min(old[i-1], a))
+#pragma unroll
+                    for (int j = KR - 1; j > 0; --j) best[j] = fmaxf(best[j], fminf(best[j - 1], a));
+                    best[0] = fmaxf(best[0], a);
+                    if (best[KR - 1] > tau_acc) { tau_acc = best[KR - 1]; improved = true; }
+                  }
+                }
               }
             }
           }
         }
       }
-      // hand the accumulator back FIRST: compaction below then overlaps the next tile's MMAs
+      const long long t_f1 = clock64();
+      dbg_filter += t_f1 - t_w1;
+      // hand the accumulator back FIRST: what follows overlaps the next MMAs
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
+      if (KR > 0 && improved) atomicMax(g_tau, okey(tau_acc * p.inv_scale));
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
-      constexpr int ROOM = 32 * (TILE_N / 32 / 2);
+      constexpr int ROOM = TILE_N;
       static_assert(C - ROOM >= 32, "candidate capacity too small for a tile");
       u32 need = __ballot_sync(FULL, cnt > C - ROOM);
       while (need) {
@@ -569,9 +628,14 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           if (t == t) atomicMax(g_tau, okey(t));
         }
         __syncwarp();
+        ++dbg_ncompact;
       }
+      dbg_compact += clock64() - t_f1;
     }
     if (cur_tp >= 0) *cnt_out = cnt;
+    if ((p.debug & 8) && blockIdx.x == 0 && lane == 0)
+      printf("[mmf debug] epilogue warp %d: %u tiles; clk per OWN tile: wait %.0f, filter %.0f, arrive+compact %.0f; %d compactions, cnt %d\n",
+             warp, tile, 2.0 * dbg_wait / tile, 2.0 * dbg_filter / tile, 2.0 * dbg_compact / tile, dbg_ncompact, cnt);
   }
 
   tcgen05_fence_before();
@@ -700,12 +764,12 @@ void mmf_mma_destroy(mmf_handle* h) {
   h->mma_state = nullptr;
 }
 
-template <bool SPLIT, int KPL, int CG>
+template <bool SPLIT, int KPL, int CG, int KR>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
                       cudaStream_t st) {
   const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
-  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG>;
+  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_pairs * CG));
@@ -734,7 +798,9 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
     return mmf_set_error(h, MMF_ERR_UNSUPPORTED, "tcgen05 path unavailable (TMA descriptor encode failed?)");
   const bool split = h->vault_mode == MMF_VAULT_FP32;
   const int npl = split ? 2 : 1;
-  const int kpl = top_k <= 32 ? 4 : top_k <= 128 ? 8 : 16;
+  // a list keeps room for a whole tile (128 appends) on top of its top_k, and compaction should be
+  // rare: C = 256 up to k = 64, else 512 (k = 100: 284 appends between compactions)
+  const int kpl = top_k <= 64 ? 8 : 16;
   const int C = 32 * kpl;
 
   MmaParams p;
@@ -760,7 +826,8 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   const size_t off_q = 65536;
   const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
-  const size_t off_cnt = off_tau + al((size_t)p.q_pad * 4);
+  const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
+  const size_t off_cnt = off_pool + al((size_t)p.q_pad * 64);
   const size_t off_cand = off_cnt + al((size_t)lists * 4);
   const size_t total = off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
@@ -770,9 +837,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.cand_cnt = (int*)(sc + off_cnt);
   p.cand = (u64*)(sc + off_cand);
   p.g_tau = (u32*)(sc + off_tau);
+  p.pool = (u32*)(sc + off_pool);
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
 
-  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau);
+  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
+                                                           p.pool, top_k);
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;
@@ -783,19 +852,19 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                   strides, box))
     return mmf_set_error(h, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query operand");
 
-#define MMF_MMA_CASE(SPLIT_, KPL_)                                                                             \
-  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
-                                               out_disc, st)                                                   \
-                 : launch_mma<SPLIT_, KPL_, 1>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
-                                               out_disc, st)
+#define MMF_MMA_CASE(SPLIT_, KPL_, KR_)                                                                             \
+  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2, KR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
+                                                    out_disc, st)                                                   \
+                 : launch_mma<SPLIT_, KPL_, 1, KR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
+                                                    out_disc, st)
   if (split) {
-    if (kpl == 4) MMF_MMA_CASE(true, 4);
-    if (kpl == 8) MMF_MMA_CASE(true, 8);
-    MMF_MMA_CASE(true, 16);
+    if (top_k <= 16) MMF_MMA_CASE(true, 8, 16);
+    if (kpl == 8) MMF_MMA_CASE(true, 8, 0);
+    MMF_MMA_CASE(true, 16, 0);
   } else {
-    if (kpl == 4) MMF_MMA_CASE(false, 4);
-    if (kpl == 8) MMF_MMA_CASE(false, 8);
-    MMF_MMA_CASE(false, 16);
+    if (top_k <= 16) MMF_MMA_CASE(false, 8, 16);
+    if (kpl == 8) MMF_MMA_CASE(false, 8, 0);
+    MMF_MMA_CASE(false, 16, 0);
   }
 #undef MMF_MMA_CASE
 }
