@@ -69,7 +69,8 @@ struct MmaParams {
   long long units;         // (q_tiles / CG) * v_tiles: one unit = CG query tiles x one vault tile
   u64* cand;               // [strip][2 column halves][CG][TILE_M][C]
   int* cand_cnt;           // [strip][2][CG][TILE_M]
-  u32* pool;               // [q_pad][16] bucket maxima (row % top_k) for top_k <= 16; min over buckets is a grid-wide bound
+  u32* pool;               // [q_pad][256] bucket maxima: slot (row % top_k) = best score key seen among those rows by
+                           // any block; top_k distinct rows, so min over the slots <= the k-th best (a grid-wide bound)
   u32* g_tau;              // [q_pad] best known lower bound of each query's k-th best (score key), shared grid-wide
   float inv_scale;         // accumulator -> score
   int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
@@ -252,7 +253,11 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
   if (lane == 0) g_tau[w] = 0;
-  if (lane < 16) pool[w * 16 + lane] = (lane < top_k) ? 0u : 0xFFFFFFFFu;   // unused buckets never win the min
+  int pool_n = 16;                                // buckets: power of two >= top_k (>= 16)
+  while (pool_n < top_k) pool_n <<= 1;
+#pragma unroll
+  for (int j = 0; j < MMF_MAX_TOP_K / 32; ++j)   // unused buckets never win the min
+    pool[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
   float v[MMF_DIM / 32], ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MMF_DIM / 32; ++j) {
@@ -476,6 +481,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const u32 tmem_empty_l = (CG == 2) ? mapa(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
     const u32 qa_full_l = (CG == 2) ? mapa(smem_u32(qa_full), 0) : smem_u32(qa_full);
     const int k = p.top_k;
+    u32 pool_mask = 15;                               // buckets - 1: power of two >= top_k, so that the
+    while ((int)pool_mask + 1 < k) pool_mask = 2 * pool_mask + 1;   // min over buckets bounds the k-th best
     const float acc_scale = 1.0f / p.inv_scale;
     float tau_acc = -INFINITY;                        // threshold in accumulator units
     float best[KR > 0 ? KR : 1];                      // KR > 0: the KR best accumulators, descending
@@ -509,7 +516,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         buf = p.cand + list * C;
         cnt_out = p.cand_cnt + list;
         g_tau = p.g_tau + qt * TILE_M + m;
-        pool = p.pool + (long long)(qt * TILE_M + m) * 16;
+        pool = p.pool + (long long)(qt * TILE_M + m) * MMF_MAX_TOP_K;
         valid_q = (qt * TILE_M + m) < p.n_queries;
         if (KR > 0) {
 #pragma unroll
@@ -589,8 +596,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 const int col = c * 32 + 4 * i + e;
                 if (!(a < tau_acc) && (!partial || col < n_cols)) {
                   buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
+                  atomicMax(pool + ((row_id0 + col) & pool_mask), okey(a * p.inv_scale));
                   if (KR > 0) {
-                    atomicMax(pool + (row_id0 + col) % (u32)k, okey(a * p.inv_scale));
                     // sorted insert, branch free: new[i] = max(old[i], min(old[i-1], a))
 #pragma unroll
                     for (int j = KR - 1; j > 0; --j) best[j] = fmaxf(best[j], fminf(best[j - 1], a));
@@ -610,6 +617,16 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
       if (KR > 0 && improved) atomicMax(g_tau, okey(tau_acc * p.inv_scale));
+      if (KR == 0 && ((tile >> 1) & 15) == 15 && valid_q) {
+        // large top_k: refresh the grid-wide bound from the bucket pool every 16th own tile (off the
+        // critical path: the accumulator has been handed back)
+        u32 mn = 0xFFFFFFFFu;
+        for (int j = 0; j <= (int)pool_mask; j += 4) {
+          const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));
+          mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
+        }
+        if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
+      }
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
       constexpr int ROOM = TILE_N;
       static_assert(C - ROOM >= 32, "candidate capacity too small for a tile");
@@ -827,7 +844,7 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const size_t off_q = 65536;
   const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
   const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
-  const size_t off_cnt = off_pool + al((size_t)p.q_pad * 64);
+  const size_t off_cnt = off_pool + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4);
   const size_t off_cand = off_cnt + al((size_t)lists * 4);
   const size_t total = off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
