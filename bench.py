@@ -49,6 +49,23 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def ncu_traffic(workload: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` summary of this workload (profiles/r01_final_<workload>.ncu_summary.txt), else None."""
+    path = os.path.join(ROOT, "profiles", f"r01_final_{workload}.ncu_summary.txt")
+    if not os.path.exists(path):
+        return None
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    with open(path) as fh:
+        for line in fh:
+            f = line.split()
+            if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in mult and seen < 2:
+                total += float(f[1]) * mult[f[2]]
+                seen += 1
+    return total if seen == 2 else None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -309,6 +326,16 @@ def main():
                 "traffic": None, "kernel": "vault search (query prep + search + top-k select)",
                 "algorithmic_bytes_per_launch": nbytes,
                 "tensor_tflops_algorithmic": 2.0 * Q * n_local * 512 / (search_ms * 1e-3) / 1e12}
+        if Q >= 16 and args.algo != "stream":
+            # the fp32-exact tcgen05 path issues 3 f16 MMA passes per score (qh.vh + qh.vl + ql.vh): that is
+            # what the tensor pipe executes, although only 2*Q*N*D is credited as algorithmic work
+            passes = 3 if mode == "fp32" else 1
+            issued = passes * roof["tensor_tflops_algorithmic"]
+            roof.update({"mma_passes": passes, "tensor_tflops_issued": issued, "tensor_frac_issued": issued / tf_peak,
+                         "tensor_frac_algorithmic": roof["tensor_tflops_algorithmic"] / tf_peak,
+                         "note": "Q=%d on the fp32-exact path is tensor-bound once the 3 passes are counted; "
+                                 "the HBM fraction is reported as the algorithmic roofline" % Q})
+    roof["traffic"] = ncu_traffic(args.workload) if world == 1 and not args.rows else None
     roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind})"
     roof["kernel_ms"] = search_ms
 

@@ -69,6 +69,8 @@ __device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8], bool bf16
 
 template <int QC, bool BF16, int KPL>
 __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamParams p) {
+  constexpr int U = (QC <= 2) ? 4 : 2; // rows per warp in flight at once: 16 (8) independent 128-bit loads per lane
+  constexpr int SUB = 4 / U;           // sub-rounds per 32-row interval (8 warps x U rows each)
   constexpr int C = 32 * KPL;          // candidate capacity per query
   constexpr int LIMIT = C - 64;        // compaction trigger (two 32-row intervals of slack)
   constexpr int NLD = BF16 ? 2 : 4;    // 128-bit loads per lane per row
@@ -107,11 +109,11 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
     u32 g_seen = 0;
     if (warp < nq && lane == 0) g_seen = *reinterpret_cast<volatile u32*>(p.g_tau + q0 + warp);
 #pragma unroll
-    for (int sub = 0; sub < 2; ++sub) {
-      const long long r0 = base + sub * 16 + warp * 2;
-      uint4 ld[2][NLD];
+    for (int sub = 0; sub < SUB; ++sub) {
+      const long long r0 = base + sub * (8 * U) + warp * U;
+      uint4 ld[U][NLD];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (r0 + u < row_end) {
           const uint4* rp = vault + (r0 + u) * ROW_U4;
 #pragma unroll
@@ -121,9 +123,9 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
           for (int c = 0; c < NLD; ++c) ld[u][c] = make_uint4(0, 0, 0, 0);
         }
       }
-      float acc[2][QC];
+      float acc[U][QC];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < U; ++u) {
         float v[16];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -147,12 +149,12 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int qi = 0; qi < QC; ++qi) acc[u][qi] = warp_sum(acc[u][qi]);
       if (lane == 0) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < U; ++u) {
           if (r0 + u < row_end) {
 #pragma unroll
             for (int qi = 0; qi < QC; ++qi) {
@@ -278,7 +280,7 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   const int qc = Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8;
   const int gy = (Q + qc - 1) / qc;
   const int kpl = top_k <= 64 ? 4 : top_k <= 192 ? 8 : 16;
-  const long long target = (long long)h->sm_count * 3;
+  const long long target = (long long)h->sm_count * 4;
   long long gx = std::max<long long>(1, (target + gy - 1) / gy);
   gx = std::min<long long>(gx, std::max<long long>(1, (h->vault_rows + 511) / 512));
   long long rows_per_cta = align_up((size_t)((h->vault_rows + gx - 1) / gx), 32);
