@@ -617,9 +617,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
       if (KR > 0 && improved) atomicMax(g_tau, okey(tau_acc * p.inv_scale));
-      if (KR == 0 && ((tile >> 1) & 15) == 15 && valid_q) {
-        // large top_k: refresh the grid-wide bound from the bucket pool every 16th own tile (off the
-        // critical path: the accumulator has been handed back)
+      if (KR == 0 && valid_q && ((tile >> 1) < 48 ? ((tile >> 1) & 1) == 1 : ((tile >> 1) & 15) == 15)) {
+        // large top_k: refresh the grid-wide bound from the bucket pool -- every 2nd own tile while the
+        // thresholds still move fast (half of all candidate events happen in the first few thousand rows),
+        // every 16th afterwards (off the critical path: the accumulator has been handed back)
         u32 mn = 0xFFFFFFFFu;
         for (int j = 0; j <= (int)pool_mask; j += 4) {
           const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));

@@ -84,6 +84,7 @@ class MisinfoForensics:
         vault_mode: str = "fp32",
         explainer=None,
         engine: Optional[Engine] = None,
+        dedup_clip_encode: bool = True,
     ):
         """Positional arguments are the reference's.  The keyword-only ones let a caller inject
         already-built producers / an in-memory vault dict (offline use, tests) and choose the
@@ -94,6 +95,9 @@ class MisinfoForensics:
         print(f"Using device: {self.device}")
         self.gemini_available = False
         self.explainer = explainer
+        # analyze() encodes the image ONCE for both the consistency and the vault step (the reference
+        # runs the CLIP image tower twice, misinfo_forensics.py:395 and :438); results are identical
+        self.dedup_clip_encode = dedup_clip_encode
 
         if roberta_tokenizer is None:
             from transformers import RobertaTokenizer
@@ -366,13 +370,23 @@ class MisinfoForensics:
             image_scores = self.analyze_image(image_path)
             say(f"  • Deepfake Probability: {image_scores['deepfake_score']:.2%}")
             say("\n[Step 3] Image-Text Consistency (CLIP)...")
-            if text:
+            shared_embed = None
+            if text and self.dedup_clip_encode and self.vault_loaded:
+                pil = self._to_pil_image(image_path)
+                inputs = self.clip_processor(text=[text], images=pil, return_tensors="pt", padding=True).to(self.device)
+                with torch.no_grad():
+                    out = self.clip_model(**inputs)
+                consistency = {"clip_similarity": self.engine.cosine_pairs(out.text_embeds, out.image_embeds).item()}
+                shared_embed = out.image_embeds
+                say(f"  • CLIP Similarity: {consistency['clip_similarity']:.4f}")
+            elif text:
                 consistency = self.analyze_consistency(text, image_path)
                 say(f"  • CLIP Similarity: {consistency['clip_similarity']:.4f}")
             else:
                 say("  • Skipped (no text provided)")
             say("\n[Step 4] Truth Vault Search (Guardian Database)...")
-            vault = self.search_vault(image_path, user_caption=text)
+            vault = self._vault_results(shared_embed, [text], 5)[0] if shared_embed is not None else \
+                self.search_vault(image_path, user_caption=text)
             if vault["vault_available"]:
                 say(f"  • Historical Discrepancy: {vault['vault_discrepancy']:.2%}")
                 if vault["matches"]:
@@ -405,6 +419,67 @@ class MisinfoForensics:
                 "scores": all_scores, "vault_matches": vault["matches"], "explanation": explanation}
 
     # ------------------------------------------------------------------ batched analyze (new surface)
+    def analyze_batch(self, texts: Sequence[Optional[str]], images: Sequence[Optional[Union[str, Image.Image]]],
+                      top_k: int = 5) -> List[Dict]:
+        """analyze() for a batch of (text, image) samples (either may be None, not both): producers run
+        per modality (one batched CLIP forward for all pairs), then ONE pass of the hot path
+        (cosine -> vault top-k -> fusion / fallback verdict) for the whole batch.  Per sample the result
+        equals analyze(text, image_path) -- same keys, same values."""
+        n = len(texts)
+        if len(images) != n:
+            raise ValueError("texts and images must have the same length")
+        head = np.zeros((n, 3), np.float32)
+        mod = np.zeros(n, np.uint8)
+        pils: List[Optional[Image.Image]] = [None] * n
+        for i, (t, im) in enumerate(zip(texts, images)):
+            if not t and im is None:
+                raise ValueError("Provide at least one of: text, image_path, or video_path")
+            if t:
+                ts = self.analyze_text(t)
+                head[i, 0], head[i, 1] = ts["ai_score"], ts["misinfo_score"]
+                mod[i] |= 1
+            if im is not None:
+                pils[i] = self._to_pil_image(im)
+                head[i, 2] = self.analyze_image(pils[i])["deepfake_score"]
+                mod[i] |= 2
+        t_emb = torch.zeros((n, 512), device=self.device)
+        i_emb = torch.zeros((n, 512), device=self.device)
+        vis = [i for i in range(n) if mod[i] & 2]
+        both = [i for i in vis if mod[i] & 1]
+        if vis:
+            i_emb[vis] = self._clip_image_embed([pils[i] for i in vis]).float()
+        if both:
+            t_emb[both] = self._clip_text_embed([texts[i] for i in both]).float()
+        out = self.score_batch(t_emb, i_emb, head, mod, top_k=top_k)
+        x = out["scores"].cpu().numpy().astype(np.float64)
+        probs, verdict, conf = out["probs"].cpu().numpy(), out["verdict"].cpu().numpy(), out["confidence"].cpu().numpy()
+        vs, vr = out["vault_scores"].cpu().numpy(), out["vault_rows"].cpu().numpy()
+        results, need = [], []
+        for i in range(n):
+            matches = self.vault.matches(vs[i], vr[i]) if (self.vault_loaded and mod[i] & 2) else []
+            scores = {"ai_score": float(x[i, 0]), "misinfo_score": float(x[i, 1]), "deepfake_score": float(x[i, 2]),
+                      "clip_similarity": float(x[i, 3]), "vault_discrepancy": float(x[i, 4]), "text_similarity": 0.0,
+                      "verdict": int(verdict[i]), "confidence": float(conf[i]),
+                      "fake_probability": float(probs[i, 1]), "real_probability": float(probs[i, 0])}
+            if texts[i] and scores["vault_discrepancy"] != 0.0 and matches:
+                need.append(i)
+            results.append({"verdict": int(verdict[i]), "verdict_text": "FAKE" if verdict[i] == 1 else "REAL",
+                            "confidence": float(conf[i]), "scores": scores, "vault_matches": matches, "explanation": ""})
+        if need:   # caption vs matched headline, one batched text encode + one cosine launch
+            emb = self._clip_text_embed([s for i in need for s in (texts[i], results[i]["vault_matches"][0]["title"])])
+            for i, sim in zip(need, self.engine.cosine_pairs(emb[0::2], emb[1::2]).tolist()):
+                results[i]["scores"]["text_similarity"] = float(sim)
+        for r in results:
+            r["explanation"] = self.generate_gemini_explanation(r["scores"], r["vault_matches"])
+        return results
+
+    def score_matrix(self, texts: Sequence[Optional[str]], images: Sequence[Optional[Union[str, Image.Image]]]) -> torch.Tensor:
+        """(M,5) fusion-judge inputs [ai, misinfo, deepfake, clip_similarity, vault_discrepancy] for a dataset,
+        computed ONCE -- what train_fusion_judge.FusionTrainingDataset.__getitem__ recomputes per sample per
+        epoch through four analyze_* calls (train_fusion_judge.py:53-104)."""
+        res = self.analyze_batch(texts, images)
+        return torch.tensor([[r["scores"][k] for k in SCORE_ORDER] for r in res], dtype=torch.float32)
+
     def score_batch(self, text_embeds, image_embeds, head_scores, modality=None, top_k: int = 5):
         """Everything downstream of the encoders for a batch, without leaving the device:
         text_embeds/image_embeds (B,512), head_scores (B,3) = [ai, misinfo, deepfake],

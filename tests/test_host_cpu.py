@@ -117,3 +117,30 @@ def test_candidate_exchange_over_gloo_world2():
     for p in procs:
         p.join(60)
     assert all(ok for _, ok, _ in res), res
+
+
+def test_sharded_vault_directory_roundtrip(tmp_path):
+    """8f rank 3: the sharded raw vault format keeps rows + metadata and maps only a rank's slice."""
+    import pickle
+    from mmf_b200 import vault_io
+    n = 1000
+    emb = np.random.default_rng(0).standard_normal((n, 512)).astype(np.float16)
+    legacy = {"image_embeddings": emb, "text_embeddings": emb, "text_contents": [f"t{i}" for i in range(n)],
+              "image_paths": [f"p{i}" for i in range(n)], "article_ids": [str(i) for i in range(n)], "metadata": {}}
+    pk = tmp_path / "guardian_embeddings.pkl"
+    with open(pk, "wb") as fh:
+        pickle.dump(legacy, fh)
+    man = vault_io.convert_pickle(str(pk), str(tmp_path / "vault"), rows_per_shard=300)
+    assert man["n_rows"] == n and len(man["shards"]) == 4 and man["dtype"] == "float16"
+    got = []
+    for rank in range(3):
+        rows, off, total = vault_io.open_vault_dir(str(tmp_path / "vault"), rank, 3)
+        lo, hi = mmf_b200.ShardPlan(n, 3).bounds(rank)
+        assert (off, total, rows.shape[0]) == (lo, n, hi - lo) and np.array_equal(rows, emb[lo:hi])
+        got.append(rows)
+    assert np.array_equal(np.concatenate(got), emb)
+    meta = vault_io.read_metadata(str(tmp_path / "vault"))
+    assert meta == oracle.read_vault_dict(legacy)[1]
+    assert vault_io.read_metadata(str(tmp_path / "vault"), [999, 3]) == [meta[999], meta[3]]
+    with pytest.raises(ValueError):
+        vault_io.save_vault_dir(str(tmp_path / "bad"), emb, [{"title": "x"}])
