@@ -104,6 +104,8 @@ struct CandidateLists {
   int k_in;
   long long list_stride;
   long long count_stride;
+  const int* slots = nullptr;   // optional (shared memory, n_lists <= MMF_SELECT_MAX_LISTS): list l lives at
+                                // lists + slots[l]*list_stride (counts + slots[l]*count_stride); null = identity
 };
 
 // One 8-bit radix-select pass over `n` keys produced by `key_at(i)`: histogram of the digit at
@@ -173,7 +175,7 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
   if (tid == 0) sm.n_staged = 0;
   if (small_lists)
     for (int l = tid; l < src.n_lists; l += nthr)
-      sm.counts[l] = src.counts ? min(src.counts[l * src.count_stride], src.k_in) : src.k_in;
+      sm.counts[l] = src.counts ? min(src.counts[(src.slots ? src.slots[l] : l) * src.count_stride], src.k_in) : src.k_in;
   __syncthreads();
   bool staged = small_lists;
   if (small_lists) {
@@ -186,7 +188,7 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
     if (src.n_lists * 2 >= nthr) {
       // many short lists: one thread per list, 8 independent loads in flight per thread
       for (int l = tid; l < src.n_lists; l += nthr) {
-        const u64* lp = src.lists + l * src.list_stride;
+        const u64* lp = src.lists + (src.slots ? src.slots[l] : l) * src.list_stride;
         const int n = sm.counts[l];
         for (int j0 = 0; j0 < n; j0 += 8) {
           u64 key[8];
@@ -202,7 +204,7 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
       const int n_chunks = src.n_lists * chunks_per_list;
       for (int c = tid >> 5; c < n_chunks; c += nthr >> 5) {
         const int l = c / chunks_per_list, j = (c - l * chunks_per_list) * 32 + lane;
-        stage(j < sm.counts[l] ? src.lists[l * src.list_stride + j] : 0ull);
+        stage(j < sm.counts[l] ? src.lists[(src.slots ? src.slots[l] : l) * src.list_stride + j] : 0ull);
       }
     }
     __syncthreads();
@@ -212,8 +214,9 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
   auto key_at = [&](long long i) -> u64 {
     if (staged) return staging[i];
     const int l = (int)(i / src.k_in), j = (int)(i % src.k_in);
-    if (src.counts && j >= src.counts[l * src.count_stride]) return 0ull;
-    return src.lists[l * src.list_stride + j];
+    const long long sl = src.slots ? src.slots[l] : l;
+    if (src.counts && j >= src.counts[sl * src.count_stride]) return 0ull;
+    return src.lists[sl * src.list_stride + j];
   };
 
   u64 prefix = 0, mask = 0;

@@ -66,7 +66,9 @@ struct MmaParams {
   u32 row_base;            // global id of row 0
   int top_k;
   int q_tiles, v_tiles;    // q_tiles is padded to a multiple of CG
-  long long units;         // (q_tiles / CG) * v_tiles: one unit = CG query tiles x one vault tile
+  // L2-aware schedule (see pair_schedule): qtp = q_tiles / CG groups of query tiles, n_aligned = seg * qtp
+  // pairs sweep [0, v_aligned) in lock-step, the other pairs share [v_aligned, v_tiles) in qtp-major order
+  int qtp, seg, n_aligned, v_aligned;
   u64* cand;               // [strip][2 column halves][CG][TILE_M][C]
   int* cand_cnt;           // [strip][2][CG][TILE_M]
   u32* pool;               // [q_pad][256] bucket maxima: slot (row % top_k) = best score key seen among those rows by
@@ -76,6 +78,36 @@ struct MmaParams {
   int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
   const uint4* q_plane0;   // plane 0 of the query operand ([q_pad][512] bf16, or fp16 hi): goes to tensor memory
 };
+
+// Which tiles a pair works on.  A vault tile is wanted by every group of query tiles (qtp of them), and
+// the vault is far bigger than L2, so WHEN the groups read it decides the DRAM traffic: with a plain
+// flattened split (the first version) pairs of different groups were at unrelated vault positions and
+// ncu showed the 10 GB vault read ~15x per search.  Here pairs are arranged as `seg` segments x qtp
+// groups: the qtp pairs of a segment start at the same vault tile and advance at the same rate (same
+// work per tile), so one of them misses in L2 and the others hit.  Pairs that do not fit this grid
+// (n_pairs - seg*qtp of them) share the tail [v_aligned, v_tiles) of the vault for all groups.
+// Every pair gets the same number of tiles (+-1).
+struct PairSchedule {
+  int n_tiles;   // tiles this pair processes
+  int tp0, vt0;  // first tile: query-tile group, vault tile
+  int v_lo, v_hi;  // vault tile range it cycles through when moving to the next group
+  int sid_base;  // strip id of (this pair, group tp) = sid_base + tp   (unique over the grid)
+};
+__host__ __device__ inline PairSchedule pair_schedule(const MmaParams& p, int pair, int n_pairs) {
+  PairSchedule s;
+  if (pair < p.n_aligned) {
+    const int t = pair % p.qtp, g = pair / p.qtp;
+    const int a = (int)((long long)g * p.v_aligned / p.seg), b = (int)((long long)(g + 1) * p.v_aligned / p.seg);
+    s.n_tiles = b - a; s.tp0 = t; s.vt0 = a; s.v_lo = a; s.v_hi = 0x7fffffff; s.sid_base = pair - t;
+  } else {
+    const int j = pair - p.n_aligned, l = n_pairs - p.n_aligned, vl = p.v_tiles - p.v_aligned;
+    const long long ul = (long long)p.qtp * vl;
+    const long long a = j * ul / l, b = (j + 1) * ul / l;
+    s.n_tiles = (int)(b - a); s.tp0 = vl ? (int)(a / vl) : 0; s.vt0 = p.v_aligned + (vl ? (int)(a % vl) : 0);
+    s.v_lo = p.v_aligned; s.v_hi = p.v_tiles; s.sid_base = p.n_aligned + j;
+  }
+  return s;
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -302,6 +334,13 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   constexpr int C = 32 * KPL;
   constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M * CG, TILE_N);
   constexpr u32 QA_COL = 2 * TILE_N;                 // TMEM columns [256,512): plane 0 of the query tile
+  // How the 8 epilogue warps share the accumulators.  PARITY (small top_k, short per-tile work): warps
+  // 0-3 own buffer 0 (even tiles), warps 4-7 buffer 1 -- two tile periods per tile hide the hand-off
+  // latencies.  Otherwise (large top_k: many candidate events per tile) both warps of a lane quarter
+  // work on EVERY tile, alternate 32-column chunks each, so an accumulator is released after half the
+  // filtering time -- the MMAs of tile i+2 wait for exactly that.
+  constexpr bool PARITY = KR > 0;
+  constexpr int EMPTY_ARRIVALS = (PARITY ? EPI_WARPS / 2 : EPI_WARPS) * CG;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -323,14 +362,13 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   const u32 rank = (CG == 2) ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int pair = blockIdx.x / CG, n_pairs = gridDim.x / CG;
-  const long long u0 = (long long)pair * p.units / n_pairs;
-  const long long u1 = (long long)(pair + 1) * p.units / n_pairs;
+  const PairSchedule sch = pair_schedule(p, pair, n_pairs);
 
   if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, (EPI_WARPS / 2) * CG); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tmem_full + s, 1); mbar_init(tmem_empty + s, EMPTY_ARRIVALS); }
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(qa_full, EPI_WARPS * CG);
@@ -355,10 +393,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     if (lane == 0) {
       u32 it = 0, strip = 0;
       int cur_tp = -1;
-      int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);      // tp: index of the group of CG query tiles
+      int tp = sch.tp0, vt = sch.vt0;      // tp: index of the group of CG query tiles
       const u32 q_full_l = (CG == 2) ? mapa(smem_u32(q_full), 0) : smem_u32(q_full);
-      for (long long u = u0; u < u1; ++u, ++vt) {
-        if (vt == p.v_tiles) { vt = 0; ++tp; }
+      for (int u = 0; u < sch.n_tiles; ++u, ++vt) {
+        if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
         if (SPLIT && tp != cur_tp) {                  // new strip: (re)load this CTA's resident ql tile (plane 1)
           cur_tp = tp;
           mbar_wait(q_empty, (strip & 1) ^ 1);
@@ -406,9 +444,9 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
       const long long t_begin = clock64();
       long long dbg_empty = 0, dbg_full = 0;
-      int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
-      for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
-        if (vt == p.v_tiles) { vt = 0; ++tp; }
+      int tp = sch.tp0, vt = sch.vt0;
+      for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
+        if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
         if (tp != cur_tp) {
           cur_tp = tp;
           if (SPLIT) mbar_wait(q_full, strip & 1);
@@ -452,7 +490,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             if (CG == 2) umma_commit_cg2(empty_bar + s); else umma_commit(empty_bar + s);   // smem slot free once these MMAs retire
             if (kb == NUM_KBLK - 1) {
               if (CG == 2) umma_commit_cg2(tmem_full + acc); else umma_commit(tmem_full + acc);   // accumulator complete
-              if (SPLIT && (u + 1 == u1 || vt + 1 == p.v_tiles)) {                                 // strip done
+              if (SPLIT && (u + 1 == sch.n_tiles || vt + 1 == sch.v_hi)) {                         // strip done
                 if (CG == 2) umma_commit_cg2(q_empty); else umma_commit(q_empty);
               }
             }
@@ -460,7 +498,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           __syncwarp();
         }
       }
-      if ((p.debug & 8) && blockIdx.x == 0 && lane == 0) {
+      if ((p.debug & 8) && blockIdx.x == 0 && lane == 0 && tile > 0) {
         mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
         const long long dt = clock64() - t_begin;
         printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block "
@@ -497,9 +535,9 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     u32 tile = 0, g_prev = 0;
     long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
     int dbg_ncompact = 0;
-    int tp = (int)(u0 / p.v_tiles), vt = (int)(u0 % p.v_tiles);
-    for (long long u = u0; u < u1; ++u, ++tile, ++vt) {
-      if (vt == p.v_tiles) { vt = 0; ++tp; }
+    int tp = sch.tp0, vt = sch.vt0;
+    for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
+      if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
       if (tp != cur_tp) {                             // new strip: flush the old one, reset state
         if (cur_tp >= 0) {
           *cnt_out = cnt;
@@ -512,7 +550,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         g_prev = 0;
         tau_acc = -INFINITY;
         const int qt = tp * CG + (int)rank;           // this CTA's query tile
-        const long long list = (((long long)(pair + tp) * 2 + half) * CG + rank) * TILE_M + m;
+        const long long list = (((long long)(sch.sid_base + tp) * 2 + half) * CG + rank) * TILE_M + m;
         buf = p.cand + list * C;
         cnt_out = p.cand_cnt + list;
         g_tau = p.g_tau + qt * TILE_M + m;
@@ -545,7 +583,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           if (lane == 0) { if (CG == 2) mbar_arrive_cluster(qa_full_l); else mbar_arrive(qa_full); }
         }
       }
-      if ((int)(tile & 1) != half) continue;          // the other warp set owns this tile
+      if (PARITY && (int)(tile & 1) != half) continue;   // the other warp set owns this tile
       // a tighter bound found by any other block / warp for this query (valid for every list of it).
       // Software-pipelined: the value loaded during the previous tile is applied now and the next
       // load is issued, so the L2 round trip never sits on the tile's critical path.
@@ -573,7 +611,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u32 row_id0 = p.row_base + (u32)row0;
       bool improved = false;
 #pragma unroll 1
-      for (int c = 0; c < ((p.debug & 1) ? 0 : TILE_N / 32); ++c) {
+      for (int c = PARITY ? 0 : half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += PARITY ? 1 : 2) {
         u32 v[32];
         tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
         tmem_wait_ld();
@@ -617,10 +655,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
       if (KR > 0 && improved) atomicMax(g_tau, okey(tau_acc * p.inv_scale));
-      if (KR == 0 && valid_q && ((tile >> 1) < 48 ? ((tile >> 1) & 1) == 1 : ((tile >> 1) & 15) == 15)) {
-        // large top_k: refresh the grid-wide bound from the bucket pool -- every 2nd own tile while the
+      if (KR == 0 && valid_q && (tile < 96 ? (tile & 3) == 3 : (tile & 31) == 31)) {
+        // large top_k: refresh the grid-wide bound from the bucket pool -- every 4th tile while the
         // thresholds still move fast (half of all candidate events happen in the first few thousand rows),
-        // every 16th afterwards (off the critical path: the accumulator has been handed back)
+        // every 32nd afterwards (off the critical path: the accumulator has been handed back)
         u32 mn = 0xFFFFFFFFu;
         for (int j = 0; j <= (int)pool_mask; j += 4) {
           const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));
@@ -629,7 +667,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
       }
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
-      constexpr int ROOM = TILE_N;
+      constexpr int ROOM = PARITY ? TILE_N : TILE_N / 2;
       static_assert(C - ROOM >= 32, "candidate capacity too small for a tile");
       u32 need = __ballot_sync(FULL, cnt > C - ROOM);
       while (need) {
@@ -673,33 +711,42 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   constexpr int C = 32 * KPL;
   __shared__ SelectSmem sel;
   __shared__ u64 staging[4096];
-  __shared__ int s_first, s_count;
+  __shared__ int slots[4 * 160];          // (strip, half) slots holding lists of this query's tile group
+  __shared__ int n_slots;
   const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
   const int tp = qt / CG, r = qt % CG;
   if (threadIdx.x == 0) {
-    int first = -1, count = 0;
-    const long long lo = (long long)tp * p.v_tiles, hi = lo + p.v_tiles;
-    for (int c = 0; c < n_pairs; ++c) {
-      const long long a = (long long)c * p.units / n_pairs, b = (long long)(c + 1) * p.units / n_pairs;
-      if (a < hi && b > lo && b > a) {
-        if (first < 0) first = c;
-        ++count;
+    int n = 0;
+    for (int c = 0; c < n_pairs; ++c) {   // every pair whose schedule touches group tp contributes its strip
+      const PairSchedule sc = pair_schedule(p, c, n_pairs);
+      if (sc.n_tiles <= 0) continue;
+      bool touches;
+      if (c < p.n_aligned) {
+        touches = sc.tp0 == tp;
+      } else {
+        const int vl = sc.v_hi - sc.v_lo;
+        const long long first = (long long)sc.tp0 * vl + (sc.vt0 - sc.v_lo), last = first + sc.n_tiles - 1;
+        touches = vl > 0 && first / vl <= tp && tp <= last / vl;
+      }
+      if (touches && n + 2 <= 4 * 160) {
+        slots[n++] = (sc.sid_base + tp) * 2;
+        slots[n++] = (sc.sid_base + tp) * 2 + 1;
       }
     }
-    s_first = first;
-    s_count = count;
+    n_slots = n;
   }
   __syncthreads();
-  // lists of this query: [strip = pair + tp][half][r][m][C], contiguous in (strip, half)
+  // lists of this query: [strip][half][r][m][C]; slot = strip*2 + half selects a block of CG*TILE_M lists
   CandidateLists src;
-  const long long base = (((long long)(s_first + tp) * 2) * CG + r) * TILE_M + m;
+  const long long base = (long long)r * TILE_M + m;
   src.lists = p.cand + base * C;
   src.counts = p.cand_cnt + base;
-  src.n_lists = 2 * s_count;
+  src.n_lists = n_slots;
   src.k_in = C;
   src.list_stride = (long long)CG * TILE_M * C;
   src.count_stride = CG * TILE_M;
+  src.slots = slots;
   block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32,
                     out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
@@ -834,10 +881,18 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.row_base = (u32)h->vault_row_offset;
   p.top_k = top_k;
   p.v_tiles = (int)((h->vault_rows + TILE_N - 1) / TILE_N);
-  p.units = (long long)(p.q_tiles / cg) * p.v_tiles;
+  p.qtp = p.q_tiles / cg;
+  const long long units = (long long)p.qtp * p.v_tiles;
   p.inv_scale = split ? (MMF_SPLIT_INV_SCALE * MMF_SPLIT_INV_SCALE) : 1.0f;
-  const int n_pairs = (int)std::min<long long>(h->sm_count / cg, p.units);
-  const long long strips = (long long)n_pairs + p.q_tiles / cg;
+  const int n_pairs = (int)std::min<long long>(h->sm_count / cg, units);
+  // L2-aware schedule: seg x qtp pairs sweep the vault in lock-step, the rest share its tail
+  p.seg = n_pairs / p.qtp;
+  p.n_aligned = p.seg * p.qtp;
+  p.v_aligned = p.n_aligned == n_pairs ? p.v_tiles
+                                       : (int)(((long long)p.n_aligned * p.v_tiles + n_pairs / 2) / n_pairs);
+  if (p.seg == 0) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; }
+  { const char* e = getenv("MMF_MMA_FLAT"); if (e && atoi(e)) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; } }
+  const long long strips = (long long)n_pairs + p.qtp;
   const long long lists = strips * 2 * cg * TILE_M;
 
   // scratch: [64 KB counters (stream kernel) | query planes | g_tau | cand_cnt | cand]
@@ -858,6 +913,7 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.pool = (u32*)(sc + off_pool);
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
 
+  MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
   mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
                                                            p.pool, top_k);
   MMF_LAUNCH_OK(h);
