@@ -48,8 +48,11 @@ constexpr int Q_RESIDENT_BYTES = (MMF_DIM / KBLK) * TILE_BYTES;   // 128 KB
 // A stage holds this CTA's share of one 128-row x 64-element vault k-block: 128/CG rows of 128 B per
 // plane (CG = CTAs per MMA: with cta_group::2 each CTA of the pair stores HALF of the B tile).
 // smem: bf16 = 12 x 16 KB (CG 1) / 16 x 8 KB (CG 2); fp32-exact = resident ql (128 KB) + 3 x 32 KB / 6 x 16 KB
-__host__ __device__ constexpr int stage_bytes(bool split, int cg) { return (split ? 2 : 1) * TILE_BYTES / cg; }
-__host__ __device__ constexpr int mma_stages(bool split, int cg) { return split ? 3 * cg : (cg == 1 ? 12 : 16); }
+// bf16 mode puts TWO k-blocks in a stage: 8 MMAs per barrier hand-off instead of 4 (a try_wait costs ~90 clk
+// even when the data is there, against 256 clk of MMA work per k-block)
+__host__ __device__ constexpr int kblk_per_stage(bool split) { return split ? 1 : 2; }
+__host__ __device__ constexpr int stage_bytes(bool split, int cg) { return (split ? 2 : 1) * TILE_BYTES / cg * kblk_per_stage(split); }
+__host__ __device__ constexpr int mma_stages(bool split, int cg) { return split ? 3 * cg : (cg == 1 ? 6 : 8); }
 __host__ __device__ constexpr int mma_smem_bytes(bool split, int cg) {
   return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg) * stage_bytes(split, cg);
 }
@@ -329,7 +332,9 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                       const MmaParams p) {
   constexpr int STAGES = mma_stages(SPLIT, CG);
   constexpr int STAGE_BYTES = stage_bytes(SPLIT, CG);
+  constexpr int KBS = kblk_per_stage(SPLIT);         // k-blocks per stage
   constexpr int PLANE_BYTES = TILE_BYTES / CG;       // one plane of this CTA's share of a B k-block
+  constexpr int KB_BYTES = STAGE_BYTES / KBS;        // one k-block (all planes) inside a stage
   constexpr int B_ROWS = TILE_N / CG;
   constexpr int C = 32 * KPL;
   constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M * CG, TILE_N);
@@ -409,25 +414,29 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ++strip;
         }
         const int brow = vt * TILE_N + (int)rank * B_ROWS;
-        for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
+        for (int kb = 0; kb < NUM_KBLK; kb += KBS, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
-          unsigned char* st = stage_smem + s * STAGE_BYTES;
           if (p.debug & 2) { if (leader) mbar_arrive(full_bar + s); continue; }
           if (leader) mbar_expect_tx(full_bar + s, STAGE_BYTES * CG);
-          if (CG == 2) {
-            const u32 fb = mapa(smem_u32(full_bar + s), 0);
-            if (SPLIT) {
-              tma_load_3d_cg2(st, &tm_b, fb, kb * KBLK, 0, brow);
-              tma_load_3d_cg2(st + PLANE_BYTES, &tm_b, fb, kb * KBLK, 1, brow);
+          const u32 fb = (CG == 2) ? mapa(smem_u32(full_bar + s), 0) : 0u;
+#pragma unroll
+          for (int j = 0; j < KBS; ++j) {
+            unsigned char* st = stage_smem + s * STAGE_BYTES + j * KB_BYTES;
+            const int kcol = (kb + j) * KBLK;
+            if (CG == 2) {
+              if (SPLIT) {
+                tma_load_3d_cg2(st, &tm_b, fb, kcol, 0, brow);
+                tma_load_3d_cg2(st + PLANE_BYTES, &tm_b, fb, kcol, 1, brow);
+              } else {
+                tma_load_2d_cg2(st, &tm_b, fb, kcol, brow);
+              }
+            } else if (SPLIT) {
+              tma_load_3d(st, &tm_b, full_bar + s, kcol, 0, brow);
+              tma_load_3d(st + PLANE_BYTES, &tm_b, full_bar + s, kcol, 1, brow);
             } else {
-              tma_load_2d_cg2(st, &tm_b, fb, kb * KBLK, brow);
+              tma_load_2d(st, &tm_b, full_bar + s, kcol, brow);
             }
-          } else if (SPLIT) {
-            tma_load_3d(st, &tm_b, full_bar + s, kb * KBLK, 0, brow);
-            tma_load_3d(st + PLANE_BYTES, &tm_b, full_bar + s, kb * KBLK, 1, brow);
-          } else {
-            tma_load_2d(st, &tm_b, full_bar + s, kb * KBLK, brow);
           }
         }
       }
@@ -442,6 +451,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u32 q_addr = smem_u32(q_smem);
       const u32 st_addr = smem_u32(stage_smem);
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
+      const bool dbg = (p.debug & 8) != 0;
       const long long t_begin = clock64();
       long long dbg_empty = 0, dbg_full = 0;
       int tp = sch.tp0, vt = sch.vt0;
@@ -454,41 +464,45 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ++strip;
         }
         const u32 acc = tile & 1;
-        const long long t_e0 = clock64();
+        const long long t_e0 = dbg ? clock64() : 0;
         if (!(p.debug & 4)) mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
         tcgen05_fence_after();
-        dbg_empty += clock64() - t_e0;
+        if (dbg) dbg_empty += clock64() - t_e0;
         const u32 d_tmem = tmem_base + acc * TILE_N;
 #pragma unroll 1
-        for (int kb = 0; kb < NUM_KBLK; ++kb, ++it) {
+        for (int kb0 = 0; kb0 < NUM_KBLK; kb0 += KBS, ++it) {
           const int s = it % STAGES;
-          const long long t_f0 = clock64();
+          const long long t_f0 = dbg ? clock64() : 0;
           if (!(p.debug & 4)) mbar_wait(full_bar + s, (it / STAGES) & 1);
           tcgen05_fence_after();
-          dbg_full += clock64() - t_f0;
-          const u64 ql = desc_hi | (u64)(((q_addr + kb * TILE_BYTES) >> 4) & 0x3FFF);
-          const u64 vb = desc_hi | (u64)(((st_addr + s * STAGE_BYTES) >> 4) & 0x3FFF);
-          const u32 qa = tmem_base + QA_COL + kb * (KBLK / 2);     // 2 elements per column
+          if (dbg) dbg_full += clock64() - t_f0;
           if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k) {      // qh.vh  (bf16 mode: q.v); A from tensor memory
-              if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
-              else umma_f16_ts(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
-            }
-            if (SPLIT) {
+            for (int j = 0; j < KBS; ++j) {
+              const int kb = kb0 + j;
+              const u64 ql = desc_hi | (u64)(((q_addr + kb * TILE_BYTES) >> 4) & 0x3FFF);
+              const u64 vb = desc_hi | (u64)(((st_addr + s * STAGE_BYTES + j * KB_BYTES) >> 4) & 0x3FFF);
+              const u32 qa = tmem_base + QA_COL + kb * (KBLK / 2);     // 2 elements per column
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k) {    // qh.vl
-                if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
-                else umma_f16_ts(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
+              for (int k = 0; k < KBLK / 16; ++k) {      // qh.vh  (bf16 mode: q.v); A from tensor memory
+                if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
+                else umma_f16_ts(d_tmem, qa + k * 8, vb + 2 * k, IDESC, (kb | k) != 0);
               }
+              if (SPLIT) {
 #pragma unroll
-              for (int k = 0; k < KBLK / 16; ++k) {    // ql.vh, ql from shared memory (+2 = 32 B = 16 elements)
-                if (CG == 2) umma_f16_cg2(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
-                else umma_f16(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+                for (int k = 0; k < KBLK / 16; ++k) {    // qh.vl
+                  if (CG == 2) umma_f16_ts_cg2(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
+                  else umma_f16_ts(d_tmem, qa + k * 8, vb + (PLANE_BYTES >> 4) + 2 * k, IDESC, 1);
+                }
+#pragma unroll
+                for (int k = 0; k < KBLK / 16; ++k) {    // ql.vh, ql from shared memory (+2 = 32 B = 16 elements)
+                  if (CG == 2) umma_f16_cg2(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+                  else umma_f16(d_tmem, ql + 2 * k, vb + 2 * k, IDESC, 1);
+                }
               }
             }
             if (CG == 2) umma_commit_cg2(empty_bar + s); else umma_commit(empty_bar + s);   // smem slot free once these MMAs retire
-            if (kb == NUM_KBLK - 1) {
+            if (kb0 + KBS == NUM_KBLK) {
               if (CG == 2) umma_commit_cg2(tmem_full + acc); else umma_commit(tmem_full + acc);   // accumulator complete
               if (SPLIT && (u + 1 == sch.n_tiles || vt + 1 == sch.v_hi)) {                         // strip done
                 if (CG == 2) umma_commit_cg2(q_empty); else umma_commit(q_empty);
@@ -502,8 +516,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
         const long long dt = clock64() - t_begin;
         printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block "
-               "(waiting: accumulator free %.1f, operands landed %.1f)\n", tile, it, dt, (double)dt / it,
-               (double)dbg_empty / it, (double)dbg_full / it);
+               "(waiting: accumulator free %.1f, operands landed %.1f)\n", tile, it * KBS, dt,
+               (double)dt / (it * KBS), (double)dbg_empty / (it * KBS), (double)dbg_full / (it * KBS));
       }
     }
   } else {
@@ -533,6 +547,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     uint4 pool_prev[4];
     bool valid_q = false;
     u32 tile = 0, g_prev = 0;
+    const bool dbg = (p.debug & 8) != 0;
     long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
     int dbg_ncompact = 0;
     int tp = sch.tp0, vt = sch.vt0;
@@ -600,10 +615,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         for (int i = 0; i < 4; ++i) pool_prev[i] = __ldcv(reinterpret_cast<const uint4*>(pool) + i);
       }
       const u32 acc = tile & 1;
-      const long long t_w0 = clock64();
+      const long long t_w0 = dbg ? clock64() : 0;
       mbar_wait(tmem_full + acc, (tile >> 1) & 1);
       tcgen05_fence_after();
-      const long long t_w1 = clock64();
+      const long long t_w1 = dbg ? clock64() : 0;
       dbg_wait += t_w1 - t_w0;
       const long long row0 = (long long)vt * TILE_N;
       const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
@@ -648,7 +663,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           }
         }
       }
-      const long long t_f1 = clock64();
+      const long long t_f1 = dbg ? clock64() : 0;
       dbg_filter += t_f1 - t_w1;
       // hand the accumulator back FIRST: what follows overlaps the next MMAs
       tcgen05_fence_before();
@@ -686,7 +701,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         __syncwarp();
         ++dbg_ncompact;
       }
-      dbg_compact += clock64() - t_f1;
+      if (dbg) dbg_compact += clock64() - t_f1;
     }
     if (cur_tp >= 0) *cnt_out = cnt;
     if ((p.debug & 8) && blockIdx.x == 0 && lane == 0)
