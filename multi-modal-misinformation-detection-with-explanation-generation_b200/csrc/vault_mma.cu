@@ -648,8 +648,14 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                 const float a = __uint_as_float(v[4 * i + e]);
                 const int col = c * 32 + 4 * i + e;
                 if (!(a < tau_acc) && (!partial || col < n_cols)) {
-                  buf[cnt++] = pack_key(a * p.inv_scale, row_id0 + col);
-                  atomicMax(pool + ((row_id0 + col) & pool_mask), okey(a * p.inv_scale));
+                  // candidate event: keep it short (a lone warp retires ~1 instruction per 4-5 clk).  The key
+                  // is the order-preserving transform without okey()'s NaN / -0.0 canonicalisation: tensor-
+                  // core NaNs are positive (they still rank first) and -0.0 only matters for tie order.
+                  const u32 ub = __float_as_uint(SPLIT ? a * p.inv_scale : a);
+                  const u32 key = ub ^ ((u32)((int)ub >> 31) | 0x80000000u);
+                  const u32 row = row_id0 + col;
+                  buf[cnt++] = ((u64)key << 32) | row;
+                  atomicMax(pool + (row & pool_mask), key);
                   if (KR > 0) {
                     // sorted insert, branch free: new[i] = max(old[i], min(old[i-1], a))
 #pragma unroll
