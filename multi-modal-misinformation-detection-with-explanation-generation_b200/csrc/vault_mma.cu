@@ -2,33 +2,45 @@
 // top-k fused into the epilogue so the (queries x rows) score matrix never leaves the SM.
 // Replaces the batched form of misinfo_forensics.py:446 (Vn @ q) and :449-450 (argsort top-k).
 //
-// Operands.  Measured on B200: with cta_group::1 an SS-form UMMA (both operands in shared memory)
-// is bound by the smem->tensor-core path (~72 B/clk: 128x128x16 takes ~116 clk, 128x256x16 ~170
-// clk), while the TS form (A in TENSOR MEMORY) runs at the 64-clk floor.  So:
-//   A = queries (M = 128 per tile), normalised by the prep kernel, RESIDENT on the SM per strip:
-//       plane 0 (bf16 q, or fp16 qh) lives in tensor memory: 256 columns, written once per
-//       strip by the epilogue threads with tcgen05.st (lane = query, 2 elements per column);
-//       fp32-exact mode also keeps plane 1 (ql, 128 KB) in shared memory, loaded by TMA.
-//   B = vault rows (N = 128 per tile), K-major 128B-swizzled [128][64] tiles streamed from HBM by
-//       TMA through an mbarrier ring (12 x 16 KB in bf16 mode; 3 x 32 KB next to ql otherwise).
+// Shape of the kernel (every choice below was measured; see DESIGN.md section 7 and tools/umma_micro.cu):
+//   * thread-block PAIRS (tcgen05 cta_group::2): one UMMA covers M = 256 queries (two query tiles,
+//     one per CTA) x N = 128 vault rows, and each CTA stores only HALF of every vault tile.  With one
+//     CTA per MMA the TMA fill plus the tensor core's operand fetch saturate the 128 B/clk shared-
+//     memory port; the pair halves that traffic.  (A single query tile falls back to CG = 1.)
+//   * A = queries, normalised by the prep kernel, RESIDENT on the SM for a whole strip:
+//       plane 0 (bf16 q, or fp16 qh) lives in TENSOR MEMORY: 256 columns, written once per strip by
+//       the epilogue threads with tcgen05.st (lane = query, 2 elements per column) -> TS-form UMMA;
+//       fp32-exact mode also keeps plane 1 (ql, 128 KB) in shared memory, loaded by TMA -> SS form.
+//   * B = vault rows, K-major 128B-swizzled [rows][64] tiles streamed by TMA through an mbarrier ring
+//       (bf16: 8 stages x 2 k-blocks x 8 KB per CTA; fp32-exact: 6 x (vh + vl = 16 KB) next to ql).
 //   MMF_VAULT_BF16: D += q.v, 4 TS-UMMA (K=16) per 64-wide k-block.
 //   MMF_VAULT_FP32: fp32-exact.  x*2^8 = hi + lo (two fp16 planes, 22+ bits), and
 //       q.v * 2^16 = qh.vh + qh.vl + ql.vh  (+ ql.vl, < 2^-22 relative, dropped)
 //     -> 8 TS + 4 SS UMMA per k-block, all into ONE fp32 TMEM accumulator; scores = D * 2^-16.
+//   * L2-aware schedule (pair_schedule): the pairs working on different query-tile groups sweep the
+//     same vault segment together, so a vault tile is fetched from DRAM by one and hit in L2 by the rest.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (whole warp runs
-// the loop in the uniform datapath, one elected lane issues), warps 2-9 = epilogue.  Pipelines:
-// smem ring (full/empty mbarriers, TMA <-> MMA) and a double-buffered TMEM accumulator
-// (tmem_full/tmem_empty, MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile
-// i+1.  TMEM: 2 x 128 accumulator columns + 256 operand columns = 512.
+// Roles (320 threads): warps 0-7 = epilogue (warp % 4 = the TMEM lane quarter it may touch), warp 8 =
+// TMA producer, warp 9 = TMEM owner + MMA issuer (the whole warp runs the loop in the uniform datapath,
+// one elected lane issues; leader CTA of the pair only).  Pipelines: smem ring (full/empty mbarriers,
+// TMA <-> MMA) and a double-buffered TMEM accumulator (tmem_full/tmem_empty, MMA <-> epilogue), so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  TMEM: 2 x 128 accumulator columns + 256 operand
+// columns = 512.  With pairs, `full`, `tmem_empty`, `q_full`, `qa_full` live in the leader (the peer
+// signals them remotely), `empty`, `tmem_full`, `q_empty` exist in both CTAs (multicast commits).
 //
-// Epilogue = streaming top-k.  TMEM lane == query, so each epilogue thread owns one query:
-// it reads 32 accumulator columns at a time (tcgen05.ld 32x32b.x32), compares them with its
-// private threshold (a lower bound of its k-th best) and appends the rare survivors to its
-// candidate list in global memory (L2-resident); a full list is compacted to the exact top-k
-// by the whole warp (topk.cuh).  A block works on "strips" (one query tile x a run of vault
-// tiles) so that state stays in registers; a merge kernel selects the final top-k per query
-// from the strips' lists.
+// Epilogue = streaming top-k.  TMEM lane == query, so each epilogue thread owns one query: it reads
+// 32 accumulator columns at a time (tcgen05.ld 32x32b.x32), compares their maximum with its private
+// threshold (a lower bound of its k-th best) and appends the rare survivors to its candidate list in
+// global memory (L2-resident).  Thresholds: exact for top_k <= 16 (the best values sorted in
+// registers), otherwise refreshed when a list is compacted (whole warp, topk.cuh); in both cases
+// tightened grid-wide through a pool of bucket maxima (pool[row % buckets]: >= top_k distinct rows, so
+// the minimum over the buckets bounds the k-th best from below).  A block works on "strips" (one group
+// of query tiles x a run of vault tiles) so that state stays in registers; a merge kernel selects the
+// final top-k per query from the strips' lists.
+//
+// Triage switches (never needed in production): env MMF_MMA_DEBUG (bit 0: skip the filter, 1: skip
+// the vault TMA, 2: skip the MMA warp's waits, 3: print in-kernel cycle counts), MMF_MMA_CG (force 1
+// or 2 CTAs per MMA), MMF_MMA_FLAT (plain flattened schedule instead of the L2-aware one).
 #include "common.cuh"
 #include "topk.cuh"
 
