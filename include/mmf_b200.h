@@ -141,6 +141,12 @@ int mmf_fusion_forward(mmf_handle* h, const float* x, int64_t n, float* out_prob
 int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modality, int64_t n, float* out_probs,
                       int32_t* out_verdict, float* out_confidence, mmf_stream_t stream);
 
+/* Host-only self check of the tcgen05 search's work decomposition for a (n_queries, n_rows) problem on a
+ * device with sm_count SMs: MMF_OK iff every (query-tile group, vault tile) unit is scheduled exactly once,
+ * strip ids are unique and the load is balanced.  Needs no GPU (used by the CPU test-suite). */
+int mmf_mma_plan_check(int64_t n_queries, int64_t n_rows, int sm_count, int64_t* out_units, int* out_pairs,
+                       int* out_cg);
+
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
 int64_t mmf_launch_count(const mmf_handle* h);
 

@@ -49,6 +49,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 namespace mmf {
 
@@ -862,6 +863,71 @@ void mmf_mma_destroy(mmf_handle* h) {
   h->mma_state = nullptr;
 }
 
+// Work decomposition of one search: CTAs per MMA, padded query tiles, vault tiles, schedule.
+static void mma_plan(int64_t n_queries, int64_t n_rows, int sm_count, MmaParams& p, int& cg, int& n_pairs) {
+  // a thread-block pair per MMA as soon as there are two query tiles to pair up
+  cg = n_queries > TILE_M ? 2 : 1;
+  { const char* e = getenv("MMF_MMA_CG"); if (e && (atoi(e) == 1 || atoi(e) == 2)) cg = atoi(e); }
+  p.n_queries = (int)n_queries;
+  p.q_tiles = (int)((n_queries + TILE_M - 1) / TILE_M);
+  p.q_tiles = (p.q_tiles + cg - 1) / cg * cg;
+  p.q_pad = p.q_tiles * TILE_M;
+  p.n_rows = n_rows;
+  p.v_tiles = (int)((n_rows + TILE_N - 1) / TILE_N);
+  p.qtp = p.q_tiles / cg;
+  const long long units = (long long)p.qtp * p.v_tiles;
+  n_pairs = (int)std::max<long long>(1, std::min<long long>(sm_count / cg, units));
+  // L2-aware schedule: seg x qtp pairs sweep the vault in lock-step, the rest share its tail
+  p.seg = n_pairs / p.qtp;
+  p.n_aligned = p.seg * p.qtp;
+  p.v_aligned = p.n_aligned == n_pairs ? p.v_tiles
+                                       : (int)(((long long)p.n_aligned * p.v_tiles + n_pairs / 2) / n_pairs);
+  if (p.seg == 0) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; }
+  { const char* e = getenv("MMF_MMA_FLAT"); if (e && atoi(e)) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; } }
+}
+
+// Host-only self check of the decomposition (no GPU needed): every (query-tile group, vault tile) unit must
+// be scheduled exactly once, strip ids must be unique and inside the candidate-list allocation.
+extern "C" int mmf_mma_plan_check(int64_t n_queries, int64_t n_rows, int sm_count, int64_t* out_units,
+                                  int* out_pairs, int* out_cg) {
+  if (n_queries <= 0 || n_rows <= 0 || sm_count <= 0) return MMF_ERR_BAD_ARG;
+  MmaParams p;
+  int cg, n_pairs;
+  mma_plan(n_queries, n_rows, sm_count, p, cg, n_pairs);
+  const long long units = (long long)p.qtp * p.v_tiles;
+  if (out_units) *out_units = units;
+  if (out_pairs) *out_pairs = n_pairs;
+  if (out_cg) *out_cg = cg;
+  if (units > (1ll << 26)) return MMF_ERR_UNSUPPORTED;          // keep the check itself cheap
+  std::vector<unsigned char> seen((size_t)units, 0);
+  std::vector<int> strip_owner((size_t)(n_pairs + p.qtp), -1);
+  int lo_tiles = 0x7fffffff, hi_tiles = 0;
+  for (int c = 0; c < n_pairs; ++c) {
+    const PairSchedule s = pair_schedule(p, c, n_pairs);
+    if (s.n_tiles < 0) return MMF_ERR_CUDA;
+    lo_tiles = std::min(lo_tiles, s.n_tiles);
+    hi_tiles = std::max(hi_tiles, s.n_tiles);
+    int tp = s.tp0, vt = s.vt0, last_tp = -1;
+    for (int u = 0; u < s.n_tiles; ++u, ++vt) {
+      if (vt == s.v_hi) { vt = s.v_lo; ++tp; }
+      if (tp < 0 || tp >= p.qtp || vt < 0 || vt >= p.v_tiles) return MMF_ERR_CUDA;
+      unsigned char& cell = seen[(size_t)tp * p.v_tiles + vt];
+      if (cell) return MMF_ERR_CUDA;                              // scheduled twice
+      cell = 1;
+      if (tp != last_tp) {
+        const int sid = s.sid_base + tp;
+        if (sid < 0 || sid >= n_pairs + p.qtp || (strip_owner[sid] != -1 && strip_owner[sid] != c)) return MMF_ERR_CUDA;
+        strip_owner[sid] = c;
+        last_tp = tp;
+      }
+    }
+  }
+  for (unsigned char v : seen)
+    if (!v) return MMF_ERR_CUDA;                                  // a unit nobody processes
+  if (hi_tiles - lo_tiles > 1 + p.qtp) return MMF_ERR_UNSUPPORTED;   // badly balanced
+  return MMF_OK;
+}
+
 template <bool SPLIT, int KPL, int CG, int KR>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
@@ -903,28 +969,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
 
   MmaParams p;
   { const char* e = getenv("MMF_MMA_DEBUG"); p.debug = e ? atoi(e) : 0; }
-  // a thread-block pair per MMA as soon as there are two query tiles to pair up
-  int cg = n_queries > TILE_M ? 2 : 1;
-  { const char* e = getenv("MMF_MMA_CG"); if (e && (atoi(e) == 1 || atoi(e) == 2)) cg = atoi(e); }
-  p.n_queries = (int)n_queries;
-  p.q_tiles = (int)((n_queries + TILE_M - 1) / TILE_M);
-  p.q_tiles = (p.q_tiles + cg - 1) / cg * cg;
-  p.q_pad = p.q_tiles * TILE_M;
-  p.n_rows = h->vault_rows;
+  int cg, n_pairs;
+  mma_plan(n_queries, h->vault_rows, h->sm_count, p, cg, n_pairs);
   p.row_base = (u32)h->vault_row_offset;
   p.top_k = top_k;
-  p.v_tiles = (int)((h->vault_rows + TILE_N - 1) / TILE_N);
-  p.qtp = p.q_tiles / cg;
-  const long long units = (long long)p.qtp * p.v_tiles;
   p.inv_scale = split ? (MMF_SPLIT_INV_SCALE * MMF_SPLIT_INV_SCALE) : 1.0f;
-  const int n_pairs = (int)std::min<long long>(h->sm_count / cg, units);
-  // L2-aware schedule: seg x qtp pairs sweep the vault in lock-step, the rest share its tail
-  p.seg = n_pairs / p.qtp;
-  p.n_aligned = p.seg * p.qtp;
-  p.v_aligned = p.n_aligned == n_pairs ? p.v_tiles
-                                       : (int)(((long long)p.n_aligned * p.v_tiles + n_pairs / 2) / n_pairs);
-  if (p.seg == 0) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; }
-  { const char* e = getenv("MMF_MMA_FLAT"); if (e && atoi(e)) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; } }
   const long long strips = (long long)n_pairs + p.qtp;
   const long long lists = strips * 2 * cg * TILE_M;
 

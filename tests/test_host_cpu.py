@@ -144,3 +144,18 @@ def test_sharded_vault_directory_roundtrip(tmp_path):
     assert vault_io.read_metadata(str(tmp_path / "vault"), [999, 3]) == [meta[999], meta[3]]
     with pytest.raises(ValueError):
         vault_io.save_vault_dir(str(tmp_path / "bad"), emb, [{"title": "x"}])
+
+
+def test_mma_schedule_covers_every_unit_once():
+    """the tcgen05 search's L2-aware work decomposition, checked on the host for many shapes"""
+    import ctypes as C
+    lib = _lib.load()
+    shapes = [(1, 1), (16, 100), (128, 5000), (129, 5000), (256, 1_000_000), (257, 999_999), (1000, 100_000),
+              (4096, 1_250_000), (4096, 10_000_000 // 8 + 77), (5000, 300), (65536, 2000), (300, 127), (300, 129)]
+    for sms in (148, 132, 8, 2, 1):
+        for nq, nr in shapes:
+            units, pairs, cg = C.c_int64(), C.c_int(), C.c_int()
+            rc = lib.mmf_mma_plan_check(nq, nr, sms, C.byref(units), C.byref(pairs), C.byref(cg))
+            assert rc == 0, (sms, nq, nr, rc, units.value, pairs.value, cg.value)
+            assert cg.value == (2 if nq > 128 else 1) and 1 <= pairs.value <= max(1, sms // cg.value)
+    assert lib.mmf_mma_plan_check(0, 5, 148, None, None, None) == -1
