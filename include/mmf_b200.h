@@ -147,6 +147,11 @@ int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modalit
 int mmf_mma_plan_check(int64_t n_queries, int64_t n_rows, int sm_count, int64_t* out_units, int* out_pairs,
                        int* out_cg);
 
+/* Host-only model of the experimental histogram bound of the tcgen05 search (env MMF_MMA_BOUND=hist, large
+ * top_k): the lower bound of the top_k-th best of `scores` (n fp32 HOST values) that the per-query score
+ * histogram yields, -inf when it yields none.  Same binning code as the kernel; needs no GPU. */
+int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, float* out_bound);
+
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
 int64_t mmf_launch_count(const mmf_handle* h);
 

@@ -46,6 +46,7 @@
 
 #include <cuda.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <new>
@@ -290,13 +291,33 @@ __host__ __device__ constexpr u32 umma_idesc(u32 fmt, u32 m, u32 n) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- score histogram (HIST variants) ---------------------------------------------------------
+// Bin of a score given its fp32 bits: sign/exponent/top-5-mantissa bits, i.e. 32 bins per octave over
+// [2^-7, 2) -> bins 0..255 (MMF_MAX_TOP_K words per query, the bucket pool's memory).  Monotone in the
+// score; everything below 2^-7 (and every negative score) falls into bin 0, which carries no bound;
+// anything >= 2 - 2^-5 (and NaN, which ranks first) falls into bin 255.
+static_assert(MMF_MAX_TOP_K == 256, "the score histogram reuses the 256-word bucket pool");
+constexpr int HIST_BIN0 = 120 * 32;      // (bits >> 18) of 2^-7
+__host__ __device__ __forceinline__ int hist_bin(u32 score_bits) {
+  const int b = ((int)score_bits >> 18) - HIST_BIN0;
+  return b < 0 ? 0 : (b > 255 ? 255 : b);
+}
+__host__ __device__ __forceinline__ float hist_edge(int bin) {   // lower edge of bin >= 1
+  const u32 u = (u32)(bin + HIST_BIN0) << 18;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  union { float f; u32 u; } c; c.u = u; return c.f;
+#endif
+}
+
 // ---- query operand prep --------------------------------------------------------------------
 // One warp per padded query row: q / ||q|| (misinfo_forensics.py:439), then the MMA operand
 // planes: bf16 (1 plane) or fp16 hi/lo of q*2^8 (2 planes, plane p at row p*q_pad + i).
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
                                                              int split, void* __restrict__ planes,
                                                              u32* __restrict__ g_tau, u32* __restrict__ pool,
-                                                             int top_k) {
+                                                             int top_k, int hist) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
@@ -305,7 +326,7 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
   while (pool_n < top_k) pool_n <<= 1;
 #pragma unroll
   for (int j = 0; j < MMF_MAX_TOP_K / 32; ++j)   // unused buckets never win the min
-    pool[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
+    pool[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (hist || j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
   float v[MMF_DIM / 32], ss = 0.f;
 #pragma unroll
   for (int j = 0; j < MMF_DIM / 32; ++j) {
@@ -339,7 +360,12 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 // sorted in registers, so its threshold is EXACT at all times (the k-th best of everything it has
 // seen) instead of being refreshed only when the list is compacted; far fewer candidates pass and
 // short lists never need a compaction.  KR = 0: lazy thresholds (large top_k).
-template <bool SPLIT, int KPL, int CG, int KR>
+// HIST (KR == 0 only, experimental, env MMF_MMA_BOUND=hist): the grid-wide bound comes from a per-query
+// HISTOGRAM of candidate scores instead of the bucket maxima.  The minimum over top_k bucket maxima sits
+// near rank top_k * H(top_k) (~700 for top_k = 100), so ~7x more elements pass the filter than a tight
+// bound would let through; the histogram bound sits at the lower edge of the bin holding the k-th best
+// counted candidate (bins = 1/32 of an octave: rank <~ 1.4 * top_k).
+template <bool SPLIT, int KPL, int CG, int KR, int HIST = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
@@ -358,6 +384,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   // work on EVERY tile, alternate 32-column chunks each, so an accumulator is released after half the
   // filtering time -- the MMAs of tile i+2 wait for exactly that.
   constexpr bool PARITY = KR > 0;
+  static_assert(!(HIST && KR > 0), "the histogram bound replaces the bucket pool of the lazy-threshold (KR == 0) variants only");
   constexpr int EMPTY_ARRIVALS = (PARITY ? EPI_WARPS / 2 : EPI_WARPS) * CG;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -668,7 +695,12 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                   const u32 key = ub ^ ((u32)((int)ub >> 31) | 0x80000000u);
                   const u32 row = row_id0 + col;
                   buf[cnt++] = ((u64)key << 32) | row;
-                  atomicMax(pool + (row & pool_mask), key);
+                  if (HIST) {
+                    const int bin = hist_bin(ub);
+                    if (bin > 0) atomicAdd(pool + bin, 1u);     // bin 0 (score < 2^-7) carries no bound
+                  } else {
+                    atomicMax(pool + (row & pool_mask), key);
+                  }
                   if (KR > 0) {
                     // sorted insert, branch free: new[i] = max(old[i], min(old[i-1], a))
 #pragma unroll
@@ -693,12 +725,43 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         // large top_k: refresh the grid-wide bound from the bucket pool -- every 4th tile while the
         // thresholds still move fast (half of all candidate events happen in the first few thousand rows),
         // every 32nd afterwards (off the critical path: the accumulator has been handed back)
-        u32 mn = 0xFFFFFFFFu;
-        for (int j = 0; j <= (int)pool_mask; j += 4) {
-          const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));
-          mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
+        if (HIST) {
+          // walk the histogram from the top, 32 bins (8 independent 128-bit loads) at a time, until top_k
+          // candidates have been counted: every counted candidate is a distinct vault row with a score >=
+          // the lower edge of its bin, so that edge is a lower bound of this query's k-th best
+          const uint4* h4 = reinterpret_cast<const uint4*>(pool);
+          u32 seen = 0;
+          int edge_bin = 0;
+#pragma unroll 1
+          for (int g = MMF_MAX_TOP_K / 4 - 8; g >= 0 && edge_bin == 0; g -= 8) {
+            uint4 x[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = __ldcv(h4 + g + i);
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+              const u32 c4[4] = {x[i].w, x[i].z, x[i].y, x[i].x};      // bins (g+i)*4+3 ... (g+i)*4
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                seen += c4[e];
+                if (edge_bin == 0 && seen >= (u32)k) edge_bin = (g + i) * 4 + 3 - e;
+              }
+            }
+          }
+          if (edge_bin > 0) {
+            const float edge = hist_edge(edge_bin);
+            if (edge * acc_scale > tau_acc) {
+              tau_acc = edge * acc_scale;
+              atomicMax(g_tau, okey(edge));
+            }
+          }
+        } else {
+          u32 mn = 0xFFFFFFFFu;
+          for (int j = 0; j <= (int)pool_mask; j += 4) {
+            const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));
+            mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
+          }
+          if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
         }
-        if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
       }
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
       constexpr int ROOM = PARITY ? TILE_N : TILE_N / 2;
@@ -928,12 +991,34 @@ extern "C" int mmf_mma_plan_check(int64_t n_queries, int64_t n_rows, int sm_coun
   return MMF_OK;
 }
 
-template <bool SPLIT, int KPL, int CG, int KR>
+// Host-only model of the HIST bound (same hist_bin / hist_edge as the kernel): the lower bound of the
+// top_k-th best of `scores` that the histogram yields, -inf when it yields none.  Used by the CPU test-suite
+// to check validity (bound <= k-th best) and tightness (rank of the bound) without a GPU.
+extern "C" int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, float* out_bound) {
+  if (!scores || n < 0 || top_k < 1 || top_k > MMF_MAX_TOP_K || !out_bound) return MMF_ERR_BAD_ARG;
+  std::vector<u32> hist(MMF_MAX_TOP_K, 0u);
+  for (int64_t i = 0; i < n; ++i) {
+    union { float f; u32 u; } c;
+    c.f = scores[i];
+    const int bin = hist_bin(c.u);
+    if (bin > 0) hist[bin]++;
+  }
+  u32 seen = 0;
+  int edge_bin = 0;
+  for (int b = MMF_MAX_TOP_K - 1; b >= 0 && edge_bin == 0; --b) {
+    seen += hist[b];
+    if (seen >= (u32)top_k) edge_bin = b;
+  }
+  *out_bound = edge_bin > 0 ? hist_edge(edge_bin) : -INFINITY;
+  return MMF_OK;
+}
+
+template <bool SPLIT, int KPL, int CG, int KR, int HIST = 0>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
                       cudaStream_t st) {
   const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
-  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR>;
+  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR, HIST>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_pairs * CG));
@@ -996,8 +1081,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
 
   MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
+  // experimental (round 2 A/B): histogram bound for the lazy-threshold variants
+  bool hist = false;
+  { const char* e = getenv("MMF_MMA_BOUND"); hist = e && (e[0] == 'h' || e[0] == '1') && top_k > 16; }
   mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
-                                                           p.pool, top_k);
+                                                           p.pool, top_k, hist ? 1 : 0);
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;
@@ -1008,19 +1096,21 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                   strides, box))
     return mmf_set_error(h, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query operand");
 
-#define MMF_MMA_CASE(SPLIT_, KPL_, KR_)                                                                             \
-  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2, KR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
-                                                    out_disc, st)                                                   \
-                 : launch_mma<SPLIT_, KPL_, 1, KR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, \
-                                                    out_disc, st)
+#define MMF_MMA_CASE(SPLIT_, KPL_, KR_, HIST_)                                                                      \
+  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2, KR_, HIST_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,      \
+                                                           out_packed, out_disc, st)                                   \
+                 : launch_mma<SPLIT_, KPL_, 1, KR_, HIST_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,      \
+                                                           out_packed, out_disc, st)
   if (split) {
-    if (top_k <= 16) MMF_MMA_CASE(true, 8, 16);
-    if (kpl == 8) MMF_MMA_CASE(true, 8, 0);
-    MMF_MMA_CASE(true, 16, 0);
+    if (top_k <= 16) MMF_MMA_CASE(true, 8, 16, 0);
+    if (hist) { if (kpl == 8) MMF_MMA_CASE(true, 8, 0, 1); MMF_MMA_CASE(true, 16, 0, 1); }
+    if (kpl == 8) MMF_MMA_CASE(true, 8, 0, 0);
+    MMF_MMA_CASE(true, 16, 0, 0);
   } else {
-    if (top_k <= 16) MMF_MMA_CASE(false, 8, 16);
-    if (kpl == 8) MMF_MMA_CASE(false, 8, 0);
-    MMF_MMA_CASE(false, 16, 0);
+    if (top_k <= 16) MMF_MMA_CASE(false, 8, 16, 0);
+    if (hist) { if (kpl == 8) MMF_MMA_CASE(false, 8, 0, 1); MMF_MMA_CASE(false, 16, 0, 1); }
+    if (kpl == 8) MMF_MMA_CASE(false, 8, 0, 0);
+    MMF_MMA_CASE(false, 16, 0, 0);
   }
 #undef MMF_MMA_CASE
 }

@@ -159,3 +159,38 @@ def test_mma_schedule_covers_every_unit_once():
             assert rc == 0, (sms, nq, nr, rc, units.value, pairs.value, cg.value)
             assert cg.value == (2 if nq > 128 else 1) and 1 <= pairs.value <= max(1, sms // cg.value)
     assert lib.mmf_mma_plan_check(0, 5, 148, None, None, None) == -1
+
+
+def test_mma_histogram_bound_is_valid_and_tight():
+    """experimental grid-wide bound of the tcgen05 search (MMF_MMA_BOUND=hist): the lower edge of the histogram bin
+    holding the k-th best counted score must never exceed the true k-th best, and must sit near rank k (the bucket
+    pool it replaces sits near rank k*H(k))"""
+    import ctypes as C
+    lib = _lib.load()
+    r = np.random.default_rng(7)
+
+    def bound(scores, k):
+        s = np.ascontiguousarray(scores, np.float32)
+        out = C.c_float()
+        assert lib.mmf_mma_hist_bound(s.ctypes.data, s.size, k, C.byref(out)) == 0
+        return out.value
+
+    for n, k, sigma in ((200_000, 100, 0.0442), (1_250_000, 100, 0.0442), (50_000, 17, 0.0442), (5_000, 256, 0.3),
+                        (300, 100, 0.01)):
+        s = (r.standard_normal(n) * sigma).astype(np.float32)
+        kth = np.sort(s)[-k]
+        b = bound(s, k)
+        assert b <= kth, (n, k, b, kth)
+        if kth >= 2.0 ** -6:                      # inside the histogram's range: within one bin (1/32 octave) of the k-th best
+            assert b > kth * (1 - 1 / 32.0) - 1e-9, (n, k, b, kth)
+            rank = int((s >= b).sum())
+            assert k <= rank <= 2 * k, (n, k, rank)
+    # edge cases: fewer than k scores, all negative, NaN / inf / huge values, exact bin edges
+    assert bound(np.array([0.5, 0.25], np.float32), 3) == -np.inf
+    assert bound(-np.abs(r.standard_normal(1000)).astype(np.float32), 5) == -np.inf
+    assert bound(np.array([np.nan, np.inf, 7.0, 0.9, 0.8], np.float32), 3) <= 7.0
+    assert bound(np.array([np.nan, np.inf, 7.0, 0.9, 0.8], np.float32), 4) <= 0.9
+    assert bound(np.array([0.5] * 10, np.float32), 10) == 0.5
+    assert bound(np.array([2.0 ** -7] * 4 + [2.0 ** -8], np.float32), 4) == -np.inf   # bin 0 carries no bound
+    assert bound(np.array([2.0 ** -7 * (1 + 1 / 32)] * 4, np.float32), 4) == np.float32(2.0 ** -7 * (1 + 1 / 32))
+    assert lib.mmf_mma_hist_bound(None, 0, 5, None) == -1
