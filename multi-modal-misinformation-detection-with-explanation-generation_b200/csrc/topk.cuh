@@ -84,6 +84,42 @@ __device__ __forceinline__ int warp_compact(u64* buf, int cnt, int k, float* tau
   return base;
 }
 
+// Screened search (approximate scores, see vault_mma.cu VAR_SCREEN): like warp_compact, but every candidate
+// whose score lies within `margin` of the k-th best survives, because the exact re-scoring may still lift it
+// into the top-k.  If more than `limit` candidates would survive, the band does not fit the list: the plain
+// top-k is kept and *overflow is set (the caller flags the search for the exact redo).
+template <int KPL>
+__device__ __forceinline__ int warp_compact_band(u64* buf, int cnt, int k, float margin, int limit, float* tau_out,
+                                                 bool* overflow) {
+  const int lane = threadIdx.x & 31;
+  if (cnt <= k) return cnt;
+  u64 key[KPL];
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const int i = r * 32 + lane;
+    key[r] = (i < cnt) ? buf[i] : 0ull;
+  }
+  __syncwarp();
+  const u64 t = warp_kth_largest<KPL>(key, k);
+  const float ts = okey_inv((u32)(t >> 32));
+  u64 cut = (u64)okey(ts - margin) << 32;
+  int n = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) n += __popc(__ballot_sync(FULL, key[r] >= cut && key[r] != 0));
+  if (n > limit) { cut = t; *overflow = true; }      // warp-uniform
+  int base = 0;
+#pragma unroll
+  for (int r = 0; r < KPL; ++r) {
+    const bool keep = key[r] >= cut && key[r] != 0;
+    const u32 m = __ballot_sync(FULL, keep);
+    if (keep) buf[base + __popc(m & ((1u << lane) - 1))] = key[r];
+    base += __popc(m);
+  }
+  __syncwarp();
+  *tau_out = ts;
+  return base;
+}
+
 // ---- block-wide exact selection ---------------------------------------------------------
 #define MMF_SELECT_MAX_LISTS 1024
 

@@ -94,6 +94,10 @@ struct MmaParams {
   float inv_scale;         // accumulator -> score
   int debug;               // perf triage only (env MMF_MMA_DEBUG): 1 = epilogue skips the filter, 2 = no vault TMA
   const uint4* q_plane0;   // plane 0 of the query operand ([q_pad][512] bf16, or fp16 hi): goes to tensor memory
+  // experimental variants only (VAR_SCREEN / VAR_GUARD), appended so that the fields above keep their offsets
+  int* ovf;                // screened search: set to 1 when a candidate band overflowed -> the guarded exact pass runs
+  float margin;            // screened search: width of the candidate band in score units (2 x error bound)
+  const float* qn;         // screened search: [q_pad][512] fp32 normalised queries (exact re-scoring)
 };
 
 // Which tiles a pair works on.  A vault tile is wanted by every group of query tiles (qtp of them), and
@@ -317,7 +321,7 @@ __host__ __device__ __forceinline__ float hist_edge(int bin) {   // lower edge o
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
                                                              int split, void* __restrict__ planes,
                                                              u32* __restrict__ g_tau, u32* __restrict__ pool,
-                                                             int top_k, int hist) {
+                                                             int top_k, int hist, float* __restrict__ qn) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
   for (int j = 0; j < MMF_DIM / 32; ++j) {
     const float x = (w < n_queries) ? v[j] / norm : 0.f;
     const long long o = (long long)w * MMF_DIM + j * 32 + lane;
+    if (qn) qn[o] = x;                              // screened search: fp32 copy for the exact re-scoring
     if (split) {
       __half* hi = reinterpret_cast<__half*>(planes);
       __half* lo = hi + (long long)q_pad * MMF_DIM;
@@ -365,7 +370,16 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 // near rank top_k * H(top_k) (~700 for top_k = 100), so ~7x more elements pass the filter than a tight
 // bound would let through; the histogram bound sits at the lower edge of the bin holding the k-th best
 // counted candidate (bins = 1/32 of an octave: rank <~ 1.4 * top_k).
-template <bool SPLIT, int KPL, int CG, int KR, int HIST = 0>
+//
+// VAR_SCREEN (fp32-exact vaults, top_k <= 16, experimental, env MMF_MMA_SCREEN=1): ONE f16 pass over the hi
+// planes only (qh.vh: a third of the tensor work and half of the HBM bytes of the 3-pass kernel) gives
+// scores within a PROVEN error bound eps of the exact ones; every element within 2*eps of the running
+// k-th best is kept, and mma_rerank_kernel re-scores the survivors exactly in fp32 from the hi+lo planes
+// and selects the top-k among them -- the result is the exact top-k, not an approximation.
+// If a band does not fit a candidate list, *p.ovf is set and the guarded (VAR_GUARD) 3-pass kernel redoes
+// the batch.
+constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4;
+template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
@@ -376,7 +390,9 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   constexpr int KB_BYTES = STAGE_BYTES / KBS;        // one k-block (all planes) inside a stage
   constexpr int B_ROWS = TILE_N / CG;
   constexpr int C = 32 * KPL;
-  constexpr u32 IDESC = umma_idesc(SPLIT ? 0u : 1u, TILE_M * CG, TILE_N);
+  constexpr bool HIST = (VAR & VAR_HIST) != 0, SCREEN = (VAR & VAR_SCREEN) != 0, GUARD = (VAR & VAR_GUARD) != 0;
+  static_assert(!(SCREEN && (SPLIT || KR == 0)), "the screening pass is the 1-plane pipeline with exact register thresholds");
+  constexpr u32 IDESC = umma_idesc((SPLIT || SCREEN) ? 0u : 1u, TILE_M * CG, TILE_N);   // operands: fp16 planes / bf16
   constexpr u32 QA_COL = 2 * TILE_N;                 // TMEM columns [256,512): plane 0 of the query tile
   // How the 8 epilogue warps share the accumulators.  PARITY (small top_k, short per-tile work): warps
   // 0-3 own buffer 0 (even tiles), warps 4-7 buffer 1 -- two tile periods per tile hide the hand-off
@@ -402,6 +418,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   // With CG = 2 the MMA issuer lives in the leader CTA (rank 0): full / tmem_empty / q_full / qa_full
   // are used in the leader only (the peer signals them remotely); empty / tmem_full / q_empty exist
   // in both CTAs and receive the leader's multicast commits.
+
+  if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;   // grid-uniform: the screened search needed no redo
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const u32 rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -468,12 +486,16 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
               if (SPLIT) {
                 tma_load_3d_cg2(st, &tm_b, fb, kcol, 0, brow);
                 tma_load_3d_cg2(st + PLANE_BYTES, &tm_b, fb, kcol, 1, brow);
+              } else if (SCREEN) {
+                tma_load_3d_cg2(st, &tm_b, fb, kcol, 0, brow);        // hi plane only
               } else {
                 tma_load_2d_cg2(st, &tm_b, fb, kcol, brow);
               }
             } else if (SPLIT) {
               tma_load_3d(st, &tm_b, full_bar + s, kcol, 0, brow);
               tma_load_3d(st + PLANE_BYTES, &tm_b, full_bar + s, kcol, 1, brow);
+            } else if (SCREEN) {
+              tma_load_3d(st, &tm_b, full_bar + s, kcol, 0, brow);
             } else {
               tma_load_2d(st, &tm_b, full_bar + s, kcol, brow);
             }
@@ -576,6 +598,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     u32 pool_mask = 15;                               // buckets - 1: power of two >= top_k, so that the
     while ((int)pool_mask + 1 < k) pool_mask = 2 * pool_mask + 1;   // min over buckets bounds the k-th best
     const float acc_scale = 1.0f / p.inv_scale;
+    const float margin_acc = SCREEN ? p.margin * acc_scale : 0.f;   // candidate band in accumulator units
+#define MMF_TAU_F (SCREEN ? tau_acc - margin_acc : tau_acc)       /* what the filter compares against */
     float tau_acc = -INFINITY;                        // threshold in accumulator units
     float best[KR > 0 ? KR : 1];                      // KR > 0: the KR best accumulators, descending
     int cnt = 0;
@@ -679,19 +703,19 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        if (!(m8 < tau_acc) && valid_q) {
+        if (!(m8 < MMF_TAU_F) && valid_q) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            if (!(mx[i] < tau_acc)) {
+            if (!(mx[i] < MMF_TAU_F)) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const float a = __uint_as_float(v[4 * i + e]);
                 const int col = c * 32 + 4 * i + e;
-                if (!(a < tau_acc) && (!partial || col < n_cols)) {
+                if (!(a < MMF_TAU_F) && (!partial || col < n_cols)) {
                   // candidate event: keep it short (a lone warp retires ~1 instruction per 4-5 clk).  The key
                   // is the order-preserving transform without okey()'s NaN / -0.0 canonicalisation: tensor-
                   // core NaNs are positive (they still rank first) and -0.0 only matters for tie order.
-                  const u32 ub = __float_as_uint(SPLIT ? a * p.inv_scale : a);
+                  const u32 ub = __float_as_uint((SPLIT || SCREEN) ? a * p.inv_scale : a);
                   const u32 key = ub ^ ((u32)((int)ub >> 31) | 0x80000000u);
                   const u32 row = row_id0 + col;
                   buf[cnt++] = ((u64)key << 32) | row;
@@ -774,7 +798,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const int n = __shfl_sync(FULL, cnt, src);
         __syncwarp();
         float t = 0.f;
-        const int kept = warp_compact<KPL>(b, n, k, &t);
+        bool band_ovf = false;
+        const int kept = SCREEN ? warp_compact_band<KPL>(b, n, k, p.margin, C - ROOM, &t, &band_ovf)
+                                : warp_compact<KPL>(b, n, k, &t);
+        if (SCREEN && band_ovf && lane == 0) *p.ovf = 1;
         if (lane == src) {
           cnt = kept;
           tau_acc = fmaxf(tau_acc, t * acc_scale);
@@ -785,6 +812,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       }
       if (dbg) dbg_compact += clock64() - t_f1;
     }
+#undef MMF_TAU_F
     if (cur_tp >= 0) *cnt_out = cnt;
     if ((p.debug & 8) && blockIdx.x == 0 && lane == 0)
       printf("[mmf debug] epilogue warp %d: %u tiles; clk per OWN tile: wait %.0f, filter %.0f, arrive+compact %.0f; %d compactions, cnt %d\n",
@@ -800,39 +828,46 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
   }
 }
 
+// Slots (strip * 2 + column half) of the candidate lists that cover query-tile group `tp`: every pair whose
+// schedule touches the group contributes its strip.  Thread 0 only; `slots` / `n_slots` in shared memory.
+constexpr int MERGE_MAX_SLOTS = 4 * 160;
+__device__ __forceinline__ void gather_slots(const MmaParams& p, int n_pairs, int tp, int* slots, int* n_slots) {
+  int n = 0;
+  for (int c = 0; c < n_pairs; ++c) {
+    const PairSchedule sc = pair_schedule(p, c, n_pairs);
+    if (sc.n_tiles <= 0) continue;
+    bool touches;
+    if (c < p.n_aligned) {
+      touches = sc.tp0 == tp;
+    } else {
+      const int vl = sc.v_hi - sc.v_lo;
+      const long long first = (long long)sc.tp0 * vl + (sc.vt0 - sc.v_lo), last = first + sc.n_tiles - 1;
+      touches = vl > 0 && first / vl <= tp && tp <= last / vl;
+    }
+    if (touches && n + 2 <= MERGE_MAX_SLOTS) {
+      slots[n++] = (sc.sid_base + tp) * 2;
+      slots[n++] = (sc.sid_base + tp) * 2 + 1;
+    }
+  }
+  *n_slots = n;
+}
+
 // One block per query: gather the strips that cover its query tile, select + sort the top-k.
-template <int KPL, int CG>
+// GUARD: runs only when the screened search flagged an overflow (*p.ovf != 0).
+template <int KPL, int CG, bool GUARD = false>
 __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
                                                         float* out_scores, long long* out_rows, u64* out_packed,
                                                         float* out_disc) {
   constexpr int C = 32 * KPL;
   __shared__ SelectSmem sel;
   __shared__ u64 staging[4096];
-  __shared__ int slots[4 * 160];          // (strip, half) slots holding lists of this query's tile group
+  __shared__ int slots[MERGE_MAX_SLOTS];  // (strip, half) slots holding lists of this query's tile group
   __shared__ int n_slots;
+  if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
   const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
   const int tp = qt / CG, r = qt % CG;
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int c = 0; c < n_pairs; ++c) {   // every pair whose schedule touches group tp contributes its strip
-      const PairSchedule sc = pair_schedule(p, c, n_pairs);
-      if (sc.n_tiles <= 0) continue;
-      bool touches;
-      if (c < p.n_aligned) {
-        touches = sc.tp0 == tp;
-      } else {
-        const int vl = sc.v_hi - sc.v_lo;
-        const long long first = (long long)sc.tp0 * vl + (sc.vt0 - sc.v_lo), last = first + sc.n_tiles - 1;
-        touches = vl > 0 && first / vl <= tp && tp <= last / vl;
-      }
-      if (touches && n + 2 <= 4 * 160) {
-        slots[n++] = (sc.sid_base + tp) * 2;
-        slots[n++] = (sc.sid_base + tp) * 2 + 1;
-      }
-    }
-    n_slots = n;
-  }
+  if (threadIdx.x == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
   __syncthreads();
   // lists of this query: [strip][half][r][m][C]; slot = strip*2 + half selects a block of CG*TILE_M lists
   CandidateLists src;
@@ -846,6 +881,105 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   src.slots = slots;
   block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32,
                     out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+                    out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
+                    out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
+                    threshold);
+}
+
+// Screened search, second half (VAR_SCREEN): one block per query.
+//   1. stage every candidate of the query whose APPROXIMATE score lies within the band below the grid-wide
+//      bound, and select the approximate top-k among them (block_select_topk, no outputs): its k-th entry T
+//      is the exact k-th best approximate score of the whole shard;
+//   2. every staged candidate with score >= T - margin is re-scored EXACTLY: fp32 dot of the fp32-normalised
+//      query with hi + lo of the vault row -- the arithmetic of the streaming kernel (vault_stream.cu), so the
+//      reported scores are bit-identical to a batch-1 search; the others are dropped;
+//   3. the exact keys are selected + sorted like any other candidate list.
+// Why this is the exact top-k: |approx - exact| <= eps = margin / 2 for every row.  k rows have approx >= T,
+// hence exact >= T - eps, so the exact k-th best is >= T - eps, and a row of the exact top-k has
+// approx >= T - 2 eps -- it is among the re-scored ones.
+template <int KPL, int CG>
+__global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int n_pairs, double threshold,
+                                                         const uint4* __restrict__ vault, float* out_scores,
+                                                         long long* out_rows, u64* out_packed, float* out_disc) {
+  constexpr int C = 32 * KPL;
+  constexpr int STAGING = 4096;
+  __shared__ SelectSmem sel;
+  __shared__ u64 staging[STAGING];
+  __shared__ int slots[MERGE_MAX_SLOTS];
+  __shared__ int n_slots;
+  const int qg = blockIdx.x;
+  const int qt = qg / TILE_M, m = qg % TILE_M;
+  const int tp = qt / CG, r = qt % CG;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
+  __syncthreads();
+  CandidateLists src;
+  const long long base = (long long)r * TILE_M + m;
+  src.lists = p.cand + base * C;
+  src.counts = p.cand_cnt + base;
+  src.n_lists = n_slots;
+  src.k_in = C;
+  src.list_stride = (long long)CG * TILE_M * C;
+  src.count_stride = CG * TILE_M;
+  src.slots = slots;
+  // g_tau bounds the k-th best APPROXIMATE score from below; candidates down to margin below it may matter
+  const u32 g = p.g_tau[qg];
+  const u64 min_key = g ? (u64)okey(okey_inv(g) - p.margin) << 32 : 0ull;
+  block_select_topk(src, p.top_k, sel, staging, STAGING, min_key, nullptr, nullptr, nullptr, nullptr, threshold);
+  const u32 n_staged = sel.n_staged;
+  if (n_staged > (u32)STAGING || n_slots >= MERGE_MAX_SLOTS) {   // band too wide to stage: exact redo of the batch
+    if (tid == 0) *p.ovf = 1;
+    return;
+  }
+  const u64 kth = sel.win[p.top_k - 1];                          // 0: fewer than top_k candidates -> keep all
+  const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - p.margin) << 32 : 0ull;
+  __syncthreads();
+
+  // this lane's 16 elements of the normalised query: 8*lane..+7 and 256+8*lane..+7 (as vault_stream.cu)
+  float q[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) q[e] = p.qn[(long long)qg * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)];
+  for (u32 i = warp; i < n_staged; i += 8) {
+    const u64 key = staging[i];
+    u64 exact = 0ull;                                            // dropped unless inside the band
+    if (key >= cut) {                                            // warp-uniform
+      const u32 row = (u32)key;
+      const uint4* rp = vault + (long long)(row - p.row_base) * 128;   // [hi 64 x uint4 | lo 64 x uint4]
+      uint4 ld[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ld[c] = __ldg(rp + c * 32 + lane);
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const u32 hx[4] = {ld[c].x, ld[c].y, ld[c].z, ld[c].w};
+        const u32 lx[4] = {ld[c + 2].x, ld[c + 2].y, ld[c + 2].z, ld[c + 2].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hx[j]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lx[j]));
+          v[c * 8 + 2 * j] = hf.x + lf.x;                        // exact: hi + lo fits 24 bits
+          v[c * 8 + 2 * j + 1] = hf.y + lf.y;
+        }
+      }
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) a = fmaf(v[e], q[e], a);
+      a = warp_sum(a);
+      exact = pack_key(a * MMF_SPLIT_INV_SCALE, row);
+    }
+    __syncwarp();
+    if (lane == 0) staging[i] = exact;
+  }
+  __syncthreads();
+  // select + sort the exact keys: one list in shared memory (staging_cap 0: the passes read it in place)
+  CandidateLists ex;
+  ex.lists = staging;
+  ex.counts = nullptr;
+  ex.n_lists = 1;
+  ex.k_in = (int)n_staged;
+  ex.list_stride = 0;
+  ex.count_stride = 0;
+  block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
                     threshold);
@@ -1013,12 +1147,12 @@ extern "C" int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, flo
   return MMF_OK;
 }
 
-template <bool SPLIT, int KPL, int CG, int KR, int HIST = 0>
+template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
                       cudaStream_t st) {
   const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
-  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR, HIST>;
+  auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR, VAR>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_pairs * CG));
@@ -1034,11 +1168,26 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   cfg.numAttrs = 1;
   MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
   h->launches++;
-  mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
-                                                          (u64*)out_packed, out_disc);
+  if constexpr ((VAR & VAR_SCREEN) != 0)
+    mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                             (long long*)out_rows, (u64*)out_packed, out_disc);
+  else if constexpr ((VAR & VAR_GUARD) != 0)
+    mma_merge_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                                  (u64*)out_packed, out_disc);
+  else
+    mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                            (u64*)out_packed, out_disc);
   MMF_LAUNCH_OK(h);
   return MMF_OK;
 }
+
+// Error bound of the screening pass (VAR_SCREEN), in score units.  With x*2^8 = hi + lo + r (fp16 hi/lo split,
+// |lo| <= 2^-11 |hi|, |r| <= 2^-11 |lo|), unit rows and unit queries:
+//   |qh.vh * 2^-16 - q.v| <= (|ql+rq| |vh| + |qh| |vl+rv| + |ql+rq| |vl+rv|) * 2^-16   (Cauchy-Schwarz)
+//                         <= 2 * 2^-11 * (1 + 2^-10) + 2^-22 < 9.78e-4,
+// plus the tensor core's fp32 accumulation error over 32 K-steps (measured 2.5e-6, budgeted 2e-5) and the fp32
+// rounding of the exact re-scoring (~2e-7).  Measured worst case on random and clustered vaults: 1.0e-4.
+constexpr float SCREEN_EPS = 1.05e-3f;
 
 int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
                    float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st) {
@@ -1069,7 +1218,12 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
   const size_t off_cnt = off_pool + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4);
   const size_t off_cand = off_cnt + al((size_t)lists * 4);
-  const size_t total = off_cand + (size_t)lists * C * 8;
+  // experimental (round 2 A/B): screened fp32-exact search, see VAR_SCREEN
+  bool screen = false;
+  { const char* e = getenv("MMF_MMA_SCREEN"); screen = e && atoi(e) != 0 && split && top_k <= 16; }
+  const size_t off_qn = off_cand + al((size_t)lists * C * 8);
+  const size_t off_flag = off_qn + (screen ? al((size_t)p.q_pad * MMF_DIM * 4) : 0);
+  const size_t total = screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* sc = (char*)h->scratch;
@@ -1079,13 +1233,17 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.g_tau = (u32*)(sc + off_tau);
   p.pool = (u32*)(sc + off_pool);
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
+  p.ovf = screen ? (int*)(sc + off_flag) : nullptr;
+  p.margin = screen ? 2.0f * SCREEN_EPS : 0.f;
+  p.qn = screen ? (const float*)(sc + off_qn) : nullptr;
 
   MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
   // experimental (round 2 A/B): histogram bound for the lazy-threshold variants
   bool hist = false;
   { const char* e = getenv("MMF_MMA_BOUND"); hist = e && (e[0] == 'h' || e[0] == '1') && top_k > 16; }
+  if (screen) MMF_CUDA_OK(h, cudaMemsetAsync(p.ovf, 0, 4, st));
   mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
-                                                           p.pool, top_k, hist ? 1 : 0);
+                                                           p.pool, top_k, hist ? 1 : 0, screen ? (float*)(sc + off_qn) : nullptr);
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;
@@ -1101,6 +1259,24 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                                                            out_packed, out_disc, st)                                   \
                  : launch_mma<SPLIT_, KPL_, 1, KR_, HIST_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,      \
                                                            out_packed, out_disc, st)
+  if (screen) {
+    // 1 pass over the hi planes + exact re-scoring of the survivors; then the guarded 3-pass search, which
+    // returns at once unless a candidate band overflowed (its bounds must restart from scratch: the
+    // screening pass published bounds on APPROXIMATE scores)
+    rc = cg == 2 ? launch_mma<false, 8, 2, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+                                                           out_packed, out_disc, st)
+                 : launch_mma<false, 8, 1, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+                                                           out_packed, out_disc, st);
+    if (rc != MMF_OK) return rc;
+    MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));
+    mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, 1, planes, p.g_tau, p.pool,
+                                                             top_k, 0, nullptr);
+    MMF_LAUNCH_OK(h);
+    return cg == 2 ? launch_mma<true, 8, 2, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+                                                           out_packed, out_disc, st)
+                   : launch_mma<true, 8, 1, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+                                                           out_packed, out_disc, st);
+  }
   if (split) {
     if (top_k <= 16) MMF_MMA_CASE(true, 8, 16, 0);
     if (hist) { if (kpl == 8) MMF_MMA_CASE(true, 8, 0, 1); MMF_MMA_CASE(true, 16, 0, 1); }

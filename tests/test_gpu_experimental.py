@@ -93,3 +93,57 @@ def test_histogram_bound_adversarial_orders(eng):
     with env(MMF_MMA_BOUND="hist"):
         got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+
+
+# ------------------------------------------------------------------------------ screened fp32-exact search
+@pytest.mark.parametrize("n_rows,nq,k", [(128, 1, 1), (129, 130, 5), (5000, 16, 10), (40000, 257, 10), (200000, 128, 16),
+                                         (150, 3, 12), (1_000_000, 256, 10)])
+def test_screened_search_is_exact(eng, n_rows, nq, k):
+    """MMF_MMA_SCREEN=1: one f16 pass over the hi planes + exact fp32 re-scoring of everything within the proven
+    error band.  The result must be the exact top-k: bit-identical to the streaming kernel (same re-scoring
+    arithmetic), and within the fp32 tolerance of the oracle."""
+    if n_rows >= 1_000_000:
+        g = torch.Generator(device="cuda").manual_seed(3)
+        vault = torch.randn(n_rows, 512, device="cuda", generator=g)
+        q = torch.randn(nq, 512, device="cuda", generator=g)
+        q[:32] = vault[torch.arange(32, device="cuda") * 31_001] + 0.3 * q[:32]
+    else:
+        vault = synth.vault_rows(n_rows, seed=n_rows + 1) * np.random.default_rng(2).uniform(0.1, 5, (n_rows, 1)).astype(np.float32)
+        q, _, _ = synth.queries(nq, n_rows, seed=nq + 11, plant_frac=0.4, vault_seed=n_rows + 1)
+    eng.vault_load(vault, mode="fp32")
+    exact = [npy(t) for t in eng.vault_search(q, k, algo="stream")]
+    with env(MMF_MMA_SCREEN="1"):
+        got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+    for a, b, what in zip(got, exact, ("scores", "rows", "discrepancy")):
+        assert np.array_equal(a, b, equal_nan=True), f"screened search: {what} differ from the streaming kernel"
+    if n_rows < 1_000_000:
+        ri, rs, rd = oracle.vault_search_batched(vault, q, k)
+        kk = ri.shape[1]
+        assert_topk(got[1][:, :kk], got[0][:, :kk], ri, rs, FP32_TOL, f"screen N={n_rows} Q={nq} k={k}")
+        assert_close(got[2], rd, FP32_TOL, "disc")
+
+
+def test_screened_search_band_overflow_falls_back(eng):
+    """thousands of identical rows: the candidate band cannot fit a list, the search flags the overflow and the
+    guarded 3-pass kernel redoes the batch -> bit-identical to the default tcgen05 result; ties: higher row id first"""
+    base = synth.vault_rows(20000, seed=31)
+    vault = np.concatenate([base[:5000], np.repeat(base[7:8], 4000, axis=0), base[5000:]])
+    q = np.stack([base[7] * 2.0, base[9], base[11] + 0.1 * base[12]] + [base[100 + i] + base[300 + i] for i in range(140)])
+    eng.vault_load(vault, mode="fp32")
+    ref = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
+    with env(MMF_MMA_SCREEN="1"):
+        got = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
+    assert list(got[1][0]) == list(range(8999, 8989, -1))
+    # moderately clustered vault (bands of a few hundred rows: no overflow expected, exact either way)
+    r = np.random.default_rng(4)
+    centres = synth.vault_rows(50, seed=32)
+    vault = centres[r.integers(0, 50, 60000)] + 0.02 * r.standard_normal((60000, 512)).astype(np.float32)
+    q = centres[:40] + 0.02 * r.standard_normal((40, 512)).astype(np.float32)
+    eng.vault_load(vault, mode="fp32")
+    exact = [npy(t) for t in eng.vault_search(q, 10, algo="stream")]
+    with env(MMF_MMA_SCREEN="1"):
+        got = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
+    ri, rs, _ = oracle.vault_search_batched(vault, q, 10)
+    assert_topk(got[1], got[0], ri, rs, FP32_TOL, "clustered vault")
+    assert_close(got[0], exact[0], 5e-6, "clustered vault vs streaming kernel")
