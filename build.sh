@@ -18,3 +18,7 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" -shared -o "$OUT" build/api.o build/cosine.o build/fusion.o build/vault_build.o build/vault_stream.o build/vault_mma.o
 echo "built $OUT"
+# torch-free C-ABI self test (tools/cabi_selftest.cu): the quick look on a GPU box
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/cabi_selftest tools/cabi_selftest.cu \
+  -L"$PKG" -lmmf_b200 -Xlinker -rpath -Xlinker "\$ORIGIN/../$PKG"
+echo "built tools/cabi_selftest"

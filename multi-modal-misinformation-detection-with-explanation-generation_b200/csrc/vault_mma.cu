@@ -1218,9 +1218,9 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
   const size_t off_cnt = off_pool + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4);
   const size_t off_cand = off_cnt + al((size_t)lists * 4);
-  // experimental (round 2 A/B): screened fp32-exact search, see VAR_SCREEN
-  bool screen = false;
-  { const char* e = getenv("MMF_MMA_SCREEN"); screen = e && atoi(e) != 0 && split && top_k <= 16; }
+  // fp32-exact vaults, top_k <= 16: screened search (VAR_SCREEN); MMF_MMA_SCREEN=0 selects the 3-pass kernel (A/B, triage)
+  bool screen = split && top_k <= 16;
+  { const char* e = getenv("MMF_MMA_SCREEN"); if (e && atoi(e) == 0) screen = false; }
   const size_t off_qn = off_cand + al((size_t)lists * C * 8);
   const size_t off_flag = off_qn + (screen ? al((size_t)p.q_pad * MMF_DIM * 4) : 0);
   const size_t total = screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
@@ -1238,9 +1238,10 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.qn = screen ? (const float*)(sc + off_qn) : nullptr;
 
   MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
-  // experimental (round 2 A/B): histogram bound for the lazy-threshold variants
-  bool hist = false;
-  { const char* e = getenv("MMF_MMA_BOUND"); hist = e && (e[0] == 'h' || e[0] == '1') && top_k > 16; }
+  // top_k > 16 (lazy thresholds): grid-wide bound from the score histogram (VAR_HIST); MMF_MMA_BOUND=pool selects the
+  // bucket maxima of round 1 (A/B, triage)
+  bool hist = top_k > 16;
+  { const char* e = getenv("MMF_MMA_BOUND"); if (e && (e[0] == 'p' || e[0] == '0')) hist = false; }
   if (screen) MMF_CUDA_OK(h, cudaMemsetAsync(p.ovf, 0, 4, st));
   mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
                                                            p.pool, top_k, hist ? 1 : 0, screen ? (float*)(sc + off_qn) : nullptr);

@@ -1,0 +1,244 @@
+// Torch-free self test of libmmf_b200.so through its C ABI (include/mmf_b200.h): default kernels against each
+// other, and the experimental variants (MMF_MMA_SCREEN, MMF_MMA_BOUND=hist) against the defaults, with timings.
+// Starts in a second (no Python), so it fits the shortest GPU slot:
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/cabi_selftest tools/cabi_selftest.cu \
+//        -Lmulti-modal-misinformation-detection-with-explanation-generation_b200 -lmmf_b200 \
+//        -Xlinker -rpath -Xlinker '$ORIGIN/../multi-modal-misinformation-detection-with-explanation-generation_b200'
+//   timeout 120 tools/cabi_selftest [rows_fp32 [rows_bf16]]
+//
+// Everything it checks is also covered by tests/ (pytest -m gpu); this is the quick look.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../include/mmf_b200.h"
+
+#define CK(x)                                                                                   \
+  do {                                                                                          \
+    cudaError_t e_ = (x);                                                                       \
+    if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } \
+  } while (0)
+#define MM(x)                                                                                   \
+  do {                                                                                          \
+    int rc_ = (x);                                                                              \
+    if (rc_ != MMF_OK) { printf("mmf error %d (%s) at %s:%d: %s\n", rc_, mmf_status_string(rc_), __FILE__, __LINE__, mmf_last_error(H)); exit(3); } \
+  } while (0)
+
+static mmf_handle* H = nullptr;
+
+__device__ __forceinline__ uint32_t hash32(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return (uint32_t)x;
+}
+// approximately normal: sum of 4 uniforms, centred (variance 1/3), times a per-row scale
+__global__ void fill_rows(float* out, long long n_rows, uint64_t seed) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * 512) return;
+  const uint32_t a = hash32(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 2), b = hash32(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 2 + 1);
+  const float u = ((a & 0xFFFF) + (a >> 16) + (b & 0xFFFF) + (b >> 16)) * (1.0f / 65536.0f) - 2.0f;
+  const float scale = 0.25f + (hash32(seed + (uint64_t)(i / 512) * 7919) & 1023) * (1.0f / 256.0f);
+  out[i] = u * scale;
+}
+// query j (j < n_plant) = vault row (j * stride) + w * noise; identical copies of row `dup_src` over [dup_lo, dup_hi)
+__global__ void plant_queries(float* q, const float* vault, int n_plant, long long stride, float w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_plant * 512) return;
+  const int j = i / 512, d = i % 512;
+  q[i] = vault[(long long)j * stride * 512 + d] * 3.0f + w * q[i];
+}
+__global__ void duplicate_rows(float* vault, long long src, long long lo, long long hi) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (hi - lo) * 512) return;
+  vault[lo * 512 + i] = vault[src * 512 + i % 512];
+}
+
+struct Result {
+  std::vector<float> scores, disc;
+  std::vector<int64_t> rows;
+};
+
+static float* d_q = nullptr;
+static float* d_scores = nullptr;
+static int64_t* d_rows = nullptr;
+static float* d_disc = nullptr;
+
+static Result search(int nq, int k, int algo, float* ms_out = nullptr, int reps = 0) {
+  MM(mmf_vault_search(H, d_q, nq, k, 0.85, algo, d_scores, d_rows, d_disc, nullptr));
+  CK(cudaDeviceSynchronize());
+  Result r;
+  r.scores.resize((size_t)nq * k); r.rows.resize((size_t)nq * k); r.disc.resize(nq);
+  CK(cudaMemcpy(r.scores.data(), d_scores, r.scores.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(r.rows.data(), d_rows, r.rows.size() * 8, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(r.disc.data(), d_disc, r.disc.size() * 4, cudaMemcpyDeviceToHost));
+  if (ms_out && reps > 0) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) MM(mmf_vault_search(H, d_q, nq, k, 0.85, algo, d_scores, d_rows, d_disc, nullptr));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < reps; ++i) MM(mmf_vault_search(H, d_q, nq, k, 0.85, algo, d_scores, d_rows, d_disc, nullptr));
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(ms_out, e0, e1));
+    *ms_out /= reps;
+  }
+  return r;
+}
+
+// bit-exact comparison; prints the first difference
+static bool same(const Result& a, const Result& b, int nq, int k, const char* what) {
+  long long bad_rows = 0, bad_scores = 0, bad_disc = 0, first = -1;
+  for (size_t i = 0; i < a.rows.size(); ++i) {
+    if (a.rows[i] != b.rows[i]) { ++bad_rows; if (first < 0) first = (long long)i; }
+    if (memcmp(&a.scores[i], &b.scores[i], 4) != 0) ++bad_scores;
+  }
+  for (int i = 0; i < nq; ++i) bad_disc += memcmp(&a.disc[i], &b.disc[i], 4) != 0;
+  printf("  %-46s rows differ %lld, scores differ %lld, discrepancy differ %lld of %d x %d -> %s\n", what, bad_rows,
+         bad_scores, bad_disc, nq, k, (bad_rows | bad_scores | bad_disc) ? "MISMATCH" : "identical");
+  if (first >= 0)
+    printf("    first: query %lld rank %lld: row %lld (%.9g) vs %lld (%.9g)\n", first / k, first % k,
+           (long long)a.rows[first], a.scores[first], (long long)b.rows[first], b.scores[first]);
+  fflush(stdout);
+  return !(bad_rows | bad_scores | bad_disc);
+}
+
+// tolerance comparison (two different kernels): scores within tol rank by rank, rows equal outside near-ties
+static bool near_equal(const Result& a, const Result& b, int nq, int k, float tol, const char* what) {
+  long long bad = 0, row_diff = 0;
+  float worst = 0.f;
+  for (int q = 0; q < nq; ++q)
+    for (int j = 0; j < k; ++j) {
+      const size_t i = (size_t)q * k + j;
+      const float d = fabsf(a.scores[i] - b.scores[i]);
+      if (!(d <= tol) && !(std::isnan(a.scores[i]) && std::isnan(b.scores[i]))) ++bad;
+      if (d > worst) worst = d;
+      if (a.rows[i] != b.rows[i]) {
+        const float g1 = j > 0 ? fabsf(b.scores[i] - b.scores[i - 1]) : 1.f, g2 = j + 1 < k ? fabsf(b.scores[i] - b.scores[i + 1]) : 0.f;
+        if (fminf(g1, g2) > 2 * tol) ++row_diff;
+      }
+    }
+  printf("  %-46s max |score diff| %.3g (tol %.0e), %lld scores off, %lld row mismatches outside near-ties -> %s\n", what,
+         worst, tol, bad, row_diff, (bad | row_diff) ? "MISMATCH" : "ok");
+  fflush(stdout);
+  return !(bad | row_diff);
+}
+
+int main(int argc, char** argv) {
+  const long long rows_fp32 = argc > 1 ? atoll(argv[1]) : 1000000;
+  const long long rows_bf16_a = argc > 2 ? atoll(argv[2]) : 1250000;
+  const long long rows_bf16_b = argc > 3 ? atoll(argv[3]) : 0;      // optional second bf16 size (e.g. 10000000)
+  int fails = 0;
+  printf("%s\n", mmf_version());
+  { int rc = mmf_create(0, &H); if (rc != MMF_OK) { printf("mmf_create failed: %s\n", mmf_status_string(rc)); return 1; } }
+  const int NQ = 4096;
+  CK(cudaMalloc(&d_q, (size_t)NQ * 512 * 4));
+  CK(cudaMalloc(&d_scores, (size_t)NQ * 256 * 4));
+  CK(cudaMalloc(&d_rows, (size_t)NQ * 256 * 8));
+  CK(cudaMalloc(&d_disc, (size_t)NQ * 4));
+  float* d_vault = nullptr;
+  long long rows_max = rows_fp32 > rows_bf16_a ? rows_fp32 : rows_bf16_a;
+  if (rows_bf16_b > rows_max) rows_max = rows_bf16_b;
+  CK(cudaMalloc(&d_vault, (size_t)rows_max * 512 * 4));
+
+  // ---------------- fp32-exact vault: stream vs 3-pass tcgen05 vs screened search (top-10, 256 queries)
+  {
+    const int nq = 256, k = 10;
+    fill_rows<<<(unsigned)((rows_fp32 * 512 + 255) / 256), 256>>>(d_vault, rows_fp32, 11);
+    fill_rows<<<(nq * 512 + 255) / 256, 256>>>(d_q, nq, 12);
+    plant_queries<<<(32 * 512 + 255) / 256, 256>>>(d_q, d_vault, 32, rows_fp32 / 32, 1.5f);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, rows_fp32, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    printf("[fp32-exact] %lld rows, %d queries, top-%d\n", rows_fp32, nq, k);
+    float ms_mma = 0, ms_screen = 0, ms_stream8 = 0;
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    Result stream = search(nq, k, MMF_ALGO_STREAM, &ms_stream8, 2);
+    Result mma = search(nq, k, MMF_ALGO_MMA, &ms_mma, 20);
+    fails += !near_equal(mma, stream, nq, k, 1e-5f, "3-pass tcgen05 vs streaming kernel");
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    Result screen = search(nq, k, MMF_ALGO_MMA, &ms_screen, 20);
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    fails += !same(screen, stream, nq, k, "screened search vs streaming kernel");
+    printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
+           rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
+    // band overflow: 3000 identical rows -> guarded 3-pass redo, ties by row id
+    duplicate_rows<<<(unsigned)((3000ll * 512 + 255) / 256), 256>>>(d_vault, 5, 70000, 73000);
+    CK(cudaMemcpy(d_q, d_vault + 5 * 512, 512 * 4, cudaMemcpyDeviceToDevice));   // query 0 = the duplicated row
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, rows_fp32, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    Result mma2 = search(nq, k, MMF_ALGO_MMA);
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    Result screen2 = search(nq, k, MMF_ALGO_MMA);
+    unsetenv("MMF_MMA_SCREEN");
+    fails += !same(screen2, mma2, nq, k, "screened search, overflowing band vs 3-pass");
+    printf("  query 0 top rows: %lld %lld %lld (expect 72999 72998 72997)\n", (long long)screen2.rows[0],
+           (long long)screen2.rows[1], (long long)screen2.rows[2]);
+    fails += screen2.rows[0] != 72999;
+  }
+
+  // ---------------- bf16 vault: bucket pool vs histogram bound (top-100, 4096 queries)
+  for (int pass = 0; pass < 2; ++pass) {
+    const int nq = 4096, k = 100;
+    const long long rows_bf16 = pass == 0 ? rows_bf16_a : rows_bf16_b;
+    if (rows_bf16 <= 0) continue;
+    fill_rows<<<(unsigned)((rows_bf16 * 512 + 255) / 256), 256>>>(d_vault, rows_bf16, 21);
+    fill_rows<<<(nq * 512 + 255) / 256, 256>>>(d_q, nq, 22);
+    plant_queries<<<(64 * 512 + 255) / 256, 256>>>(d_q, d_vault, 64, rows_bf16 / 64, 1.5f);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, rows_bf16, 512, MMF_F32, MMF_VAULT_BF16, 0));
+    printf("[bf16] %lld rows, %d queries, top-%d\n", rows_bf16, nq, k);
+    float ms_pool = 0, ms_hist = 0;
+    setenv("MMF_MMA_BOUND", "pool", 1);
+    Result pool = search(nq, k, MMF_ALGO_MMA, &ms_pool, 10);
+    setenv("MMF_MMA_BOUND", "hist", 1);
+    Result hist = search(nq, k, MMF_ALGO_MMA, &ms_hist, 10);
+    unsetenv("MMF_MMA_BOUND");
+    fails += !same(hist, pool, nq, k, "histogram bound vs bucket pool");
+    const double fl = 2.0 * nq * rows_bf16 * 512;
+    printf("  search time: bucket pool %.3f ms (%.0f TFLOP/s), histogram %.3f ms (%.0f TFLOP/s)\n", ms_pool,
+           fl / ms_pool * 1e-9, ms_hist, fl / ms_hist * 1e-9);
+  }
+  // ---------------- sweep of small / ragged shapes (those of tests/test_gpu_parity.py), both variants, explicit switches
+  {
+    struct Shape { long long n; int nq, k; long long off; };
+    const Shape shapes[] = {{1, 1, 1, 0}, {31, 3, 5, 0}, {128, 1, 1, 0}, {129, 130, 5, 0}, {150, 3, 12, 7}, {150, 3, 200, 0},
+                            {1000, 1, 10, 0}, {2000, 40, 256, 0}, {3000, 64, 256, 100}, {4099, 2, 7, 0}, {5000, 16, 10, 0},
+                            {20000, 160, 5, 0}, {30011, 19, 10, 15005}, {33333, 300, 100, 0}, {40000, 257, 10, 0},
+                            {65536, 200, 16, 0}, {70001, 129, 17, 3}, {100000, 33, 10, 0}, {200000, 128, 32, 0},
+                            {300000, 513, 100, 1000000}, {262144, 1024, 10, 0}, {50000, 4096, 5, 0}};
+    printf("[sweep] screened / histogram variants vs the streaming kernel and the round-1 defaults\n");
+    for (const Shape& sh : shapes) {
+      fill_rows<<<(unsigned)((sh.n * 512 + 255) / 256), 256>>>(d_vault, sh.n, 100 + sh.n);
+      fill_rows<<<(sh.nq * 512 + 255) / 256, 256>>>(d_q, sh.nq, 200 + sh.nq);
+      const int n_plant = sh.nq < 8 ? 1 : sh.nq / 8;
+      plant_queries<<<(n_plant * 512 + 255) / 256, 256>>>(d_q, d_vault, n_plant, sh.n / n_plant > 0 ? sh.n / n_plant : 0, 1.0f);
+      CK(cudaDeviceSynchronize());
+      char what[96];
+      for (int mode = 0; mode < 2; ++mode) {
+        MM(mmf_vault_load(H, d_vault, 1, sh.n, 512, MMF_F32, mode == 0 ? MMF_VAULT_FP32 : MMF_VAULT_BF16, sh.off));
+        setenv("MMF_MMA_SCREEN", "0", 1);
+        setenv("MMF_MMA_BOUND", "pool", 1);
+        Result base = search(sh.nq, sh.k, MMF_ALGO_MMA);
+        setenv("MMF_MMA_SCREEN", "1", 1);
+        setenv("MMF_MMA_BOUND", "hist", 1);
+        Result var = search(sh.nq, sh.k, MMF_ALGO_MMA);
+        snprintf(what, sizeof what, "%s N=%lld Q=%d k=%d off=%lld", mode ? "bf16" : "fp32", sh.n, sh.nq, sh.k, sh.off);
+        if (mode == 0 && sh.k <= 16) {
+          Result stream = search(sh.nq, sh.k, MMF_ALGO_STREAM);
+          fails += !same(var, stream, sh.nq, sh.k, what);
+          fails += !near_equal(base, stream, sh.nq, sh.k, 1e-5f, "   (3-pass vs streaming kernel)");
+        } else {
+          fails += !same(var, base, sh.nq, sh.k, what);
+        }
+      }
+    }
+    unsetenv("MMF_MMA_SCREEN");
+    unsetenv("MMF_MMA_BOUND");
+  }
+  printf("launches: %lld; %s\n", (long long)mmf_launch_count(H), fails ? "SELFTEST FAILED" : "selftest ok");
+  mmf_destroy(H);
+  return fails ? 1 : 0;
+}
