@@ -49,10 +49,10 @@ def peaks():
     return 6650.0, 1590.0, 1400.0, "fallback"
 
 
-def ncu_traffic(workload: str):
+def ncu_traffic(summary: str):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` summary of this workload (profiles/r01_final_<workload>.ncu_summary.txt), else None."""
-    path = os.path.join(ROOT, "profiles", f"r01_final_{workload}.ncu_summary.txt")
+    `ncu --set full` summary of this workload / kernel variant (profiles/<summary>.ncu_summary.txt), else None."""
+    path = os.path.join(ROOT, "profiles", f"{summary}.ncu_summary.txt")
     if not os.path.exists(path):
         return None
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
@@ -327,15 +327,30 @@ def main():
                 "algorithmic_bytes_per_launch": nbytes,
                 "tensor_tflops_algorithmic": 2.0 * Q * n_local * 512 / (search_ms * 1e-3) / 1e12}
         if Q >= 16 and args.algo != "stream":
-            # the fp32-exact tcgen05 path issues 3 f16 MMA passes per score (qh.vh + qh.vl + ql.vh): that is
-            # what the tensor pipe executes, although only 2*Q*N*D is credited as algorithmic work
-            passes = 3 if mode == "fp32" else 1
+            # fp32-exact tcgen05 path.  top_k <= 16 (default): SCREENED search -- one f16 pass over the hi planes
+            # (half of the stored bytes, a third of the MMA work), then exact fp32 re-scoring of the rows inside the
+            # proven error band.  Otherwise / MMF_MMA_SCREEN=0: 3 f16 passes (qh.vh + qh.vl + ql.vh).
+            # Only 2*Q*N*D flop and N*D*4 bytes are credited as algorithmic work either way.
+            screened = mode == "fp32" and K <= 16 and os.environ.get("MMF_MMA_SCREEN", "1") != "0"
+            passes = 3 if (mode == "fp32" and not screened) else 1
             issued = passes * roof["tensor_tflops_algorithmic"]
+            streamed = float(n_local) * 512 * (2 if (screened or mode == "bf16") else 4)
             roof.update({"mma_passes": passes, "tensor_tflops_issued": issued, "tensor_frac_issued": issued / tf_peak,
                          "tensor_frac_algorithmic": roof["tensor_tflops_algorithmic"] / tf_peak,
-                         "note": "Q=%d on the fp32-exact path is tensor-bound once the 3 passes are counted; "
-                                 "the HBM fraction is reported as the algorithmic roofline" % Q})
-    roof["traffic"] = ncu_traffic(args.workload) if world == 1 and not args.rows else None
+                         "variant": "screened (hi-plane pass + exact re-scoring)" if screened else "%d-pass" % passes,
+                         "bytes_streamed_per_launch": streamed,
+                         "hbm_frac_streamed": streamed / (search_ms * 1e-3) / 1e9 / hbm_peak,
+                         "note": ("the screened search streams only the fp16 hi planes (N*D*2 bytes) and re-scores the few rows "
+                                  "inside the error band from hi+lo; `achieved`/`frac` credit the algorithmic N*D*4 bytes, "
+                                  "`hbm_frac_streamed` is what DRAM actually delivers") if screened else
+                                 ("Q=%d on the 3-pass fp32-exact path is tensor-bound once the 3 passes are counted; "
+                                  "the HBM fraction is reported as the algorithmic roofline" % Q)})
+            if screened:
+                roof["ncu_summary"] = "r01_final_c2_screen"
+    # committed `ncu --set full` summary of the kernel variant that ran (profiles/): the 3-pass / bucket-pool
+    # captures of earlier revisions do not describe the screened / histogram kernels
+    summary = roof.pop("ncu_summary", "r01_final_c4_hist" if args.workload == "c4" else "r01_final_" + args.workload)
+    roof["traffic"] = ncu_traffic(summary) if world == 1 and not args.rows else None
     roof["peak_source"] = f"MEASURED_PEAKS.json ({peak_kind})"
     roof["kernel_ms"] = search_ms
 

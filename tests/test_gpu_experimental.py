@@ -1,10 +1,11 @@
-"""Parity of EXPERIMENTAL kernel variants that are compiled in but off by default (selected by an
-environment variable read at search time).  They were written when no GPU time was left in the round,
-so they are skipped unless MMF_EXPERIMENTAL=1; the first GPU session of the next round runs
+"""A/B parity of the kernel variants selected by environment switches read at search time: the screened
+fp32-exact search (default; MMF_MMA_SCREEN=0 = the 3-pass kernel) and the histogram bound (default;
+MMF_MMA_BOUND=pool = the bucket maxima of the first revisions).  The same comparisons were run on a B200 through
+the torch-free tools/cabi_selftest (profiles/r01_cabi_selftest.log: 48 bit-identical, 17 within tolerance); this
+Python form of them was written when the round's GPU time was spent and has not run on a GPU yet, so it is
+skipped unless MMF_EXPERIMENTAL=1:
 
-    MMF_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -x -q
-
-and, once green and measured faster (tools/ab_experimental.py), flips the defaults."""
+    MMF_EXPERIMENTAL=1 python -m pytest tests/test_gpu_experimental.py -x -q"""
 import contextlib
 import os
 
@@ -57,8 +58,9 @@ def test_histogram_bound_equals_bucket_pool(eng, mode, n_rows, nq, k):
     vault = synth.vault_rows(n_rows, seed=n_rows + 3) * np.random.default_rng(3).uniform(0.1, 5, (n_rows, 1)).astype(np.float32)
     q, _, _ = synth.queries(nq, n_rows, seed=nq + 13, plant_frac=0.4, vault_seed=n_rows + 3)
     eng.vault_load(vault, mode=mode)
-    base = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
-    with env(MMF_MMA_BOUND="hist"):
+    with env(MMF_MMA_BOUND="pool", MMF_MMA_SCREEN="0"):
+        base = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+    with env(MMF_MMA_BOUND="hist", MMF_MMA_SCREEN="0"):
         got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
     for a, b, what in zip(got, base, ("scores", "rows", "discrepancy")):
         assert np.array_equal(a, b, equal_nan=True), f"{what} differ between the histogram and the bucket-pool bound"
@@ -81,7 +83,8 @@ def test_histogram_bound_adversarial_orders(eng):
     q = np.stack([base, -base, base + 0.5 * noise[0], noise[1] * 1e-3] + [noise[i] for i in range(2, 140)])
     for mode, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
         eng.vault_load(vault, mode=mode)
-        ref = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+        with env(MMF_MMA_BOUND="pool"):
+            ref = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
         with env(MMF_MMA_BOUND="hist"):
             got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref)), mode
@@ -89,7 +92,8 @@ def test_histogram_bound_adversarial_orders(eng):
         assert_close(got[0], rs, tol, f"adversarial {mode}")
     dup = np.repeat(vault[:7], 3000, axis=0)                                  # 3000 copies of each row: ties everywhere
     eng.vault_load(dup, mode="fp32")
-    ref = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+    with env(MMF_MMA_BOUND="pool"):
+        ref = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
     with env(MMF_MMA_BOUND="hist"):
         got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))
@@ -130,7 +134,8 @@ def test_screened_search_band_overflow_falls_back(eng):
     vault = np.concatenate([base[:5000], np.repeat(base[7:8], 4000, axis=0), base[5000:]])
     q = np.stack([base[7] * 2.0, base[9], base[11] + 0.1 * base[12]] + [base[100 + i] + base[300 + i] for i in range(140)])
     eng.vault_load(vault, mode="fp32")
-    ref = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
+    with env(MMF_MMA_SCREEN="0"):
+        ref = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
     with env(MMF_MMA_SCREEN="1"):
         got = [npy(t) for t in eng.vault_search(q, 10, algo="mma")]
     assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref))

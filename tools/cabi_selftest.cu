@@ -5,7 +5,9 @@
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/cabi_selftest tools/cabi_selftest.cu \
 //        -Lmulti-modal-misinformation-detection-with-explanation-generation_b200 -lmmf_b200 \
 //        -Xlinker -rpath -Xlinker '$ORIGIN/../multi-modal-misinformation-detection-with-explanation-generation_b200'
-//   timeout 120 tools/cabi_selftest [rows_fp32 [rows_bf16]]
+//   timeout 120 tools/cabi_selftest [rows_fp32 [rows_bf16 [rows_bf16_b]]]
+//   ncu --set full --clock-control none --import-source on -k regex:vault_mma_topk -c 3 -o x tools/cabi_selftest profile
+//        (one C2-shaped screened search + its guarded no-op + one C4-shard-shaped histogram search)
 //
 // Everything it checks is also covered by tests/ (pytest -m gpu); this is the quick look.
 #include <cuda_runtime.h>
@@ -128,7 +130,7 @@ static bool near_equal(const Result& a, const Result& b, int nq, int k, float to
 }
 
 int main(int argc, char** argv) {
-  const long long rows_fp32 = argc > 1 ? atoll(argv[1]) : 1000000;
+  const long long rows_fp32 = (argc > 1 && strcmp(argv[1], "profile")) ? atoll(argv[1]) : 1000000;
   const long long rows_bf16_a = argc > 2 ? atoll(argv[2]) : 1250000;
   const long long rows_bf16_b = argc > 3 ? atoll(argv[3]) : 0;      // optional second bf16 size (e.g. 10000000)
   int fails = 0;
@@ -144,6 +146,20 @@ int main(int argc, char** argv) {
   if (rows_bf16_b > rows_max) rows_max = rows_bf16_b;
   CK(cudaMalloc(&d_vault, (size_t)rows_max * 512 * 4));
 
+  if (argc > 1 && !strcmp(argv[1], "profile")) {     // one launch of each flagship kernel, for ncu
+    fill_rows<<<(unsigned)((1000000ll * 512 + 255) / 256), 256>>>(d_vault, 1000000, 11);
+    fill_rows<<<(4096 * 512 + 255) / 256, 256>>>(d_q, 4096, 12);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, 1000000, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    search(256, 10, MMF_ALGO_MMA);
+    fill_rows<<<(unsigned)((1250000ll * 512 + 255) / 256), 256>>>(d_vault, 1250000, 21);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, 1250000, 512, MMF_F32, MMF_VAULT_BF16, 0));
+    search(4096, 100, MMF_ALGO_MMA);
+    printf("profile mode: 2 searches done\n");
+    mmf_destroy(H);
+    return 0;
+  }
   // ---------------- fp32-exact vault: stream vs 3-pass tcgen05 vs screened search (top-10, 256 queries)
   {
     const int nq = 256, k = 10;
