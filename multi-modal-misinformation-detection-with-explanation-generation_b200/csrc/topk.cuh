@@ -300,4 +300,84 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
   __syncthreads();
 }
 
+
+// ---- fast tail (experimental, env MMF_MERGE_FAST=1; see mma_merge_kernel<.., FAST>) ---------------------
+// The three steps of block_select_topk as separate pieces, so that a kernel can stage once and pick the
+// cheapest selection for what was staged.
+
+// Step 1: the staging sweep of block_select_topk.  Returns the number of candidates that passed `min_key`
+// (they are in staging[0..n) only if n <= staging_cap).  All threads of the block must call it;
+// src.n_lists <= MMF_SELECT_MAX_LISTS.
+__device__ __forceinline__ u32 stage_candidates(const CandidateLists& src, SelectSmem& sm, u64* staging, int staging_cap,
+                                                u64 min_key) {
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31;
+  if (tid == 0) sm.n_staged = 0;
+  for (int l = tid; l < src.n_lists; l += nthr)
+    sm.counts[l] = src.counts ? min(src.counts[(src.slots ? src.slots[l] : l) * src.count_stride], src.k_in) : src.k_in;
+  __syncthreads();
+  auto stage = [&](u64 key) {
+    if (key != 0 && key >= min_key) {
+      const u32 pos = atomicAdd(&sm.n_staged, 1u);
+      if (pos < (u32)staging_cap) staging[pos] = key;
+    }
+  };
+  if (src.n_lists * 2 >= nthr) {
+    for (int l = tid; l < src.n_lists; l += nthr) {
+      const u64* lp = src.lists + (src.slots ? src.slots[l] : l) * src.list_stride;
+      const int n = sm.counts[l];
+      for (int j0 = 0; j0 < n; j0 += 8) {
+        u64 key[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) key[e] = (j0 + e < n) ? lp[j0 + e] : 0ull;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) stage(key[e]);
+      }
+    }
+  } else {
+    const int chunks_per_list = (src.k_in + 31) >> 5;
+    const int n_chunks = src.n_lists * chunks_per_list;
+    for (int c = tid >> 5; c < n_chunks; c += nthr >> 5) {
+      const int l = c / chunks_per_list, j = (c - l * chunks_per_list) * 32 + lane;
+      stage(j < sm.counts[l] ? src.lists[(src.slots ? src.slots[l] : l) * src.list_stride + j] : 0ull);
+    }
+  }
+  __syncthreads();
+  return sm.n_staged;
+}
+
+// Step 3: sm.win[0..top_k) (sorted descending, 0 = empty) -> the output arrays, as block_select_topk writes them.
+__device__ __forceinline__ void write_topk_outputs(SelectSmem& sm, int top_k, float* out_scores, long long* out_rows,
+                                                   u64* out_packed, float* out_disc, double threshold) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < top_k; i += nthr) {
+    const u64 key = sm.win[i];
+    if (out_packed) out_packed[i] = key;
+    if (out_scores) out_scores[i] = key ? okey_inv((u32)(key >> 32)) : __int_as_float(0x7FC00000);
+    if (out_rows) out_rows[i] = key ? (long long)(u32)key : -1ll;
+  }
+  if (tid == 0 && out_disc) {
+    const u64 key = sm.win[0];
+    *out_disc = key ? discrepancy_rule(okey_inv((u32)(key >> 32)), threshold) : 0.0f;
+  }
+  __syncthreads();
+}
+
+// Step 2 for SHORT inputs: rank by counting.  keys[0..n) in shared memory, unique, 0 = empty.  Every thread
+// ranks its keys against all others (n broadcast reads each) and drops the winners straight into their
+// sorted slot: two barriers instead of the 8 radix passes + bitonic sort.  sm.win[0..top_k) on return.
+__device__ __forceinline__ void block_rank_select(const u64* keys, int n, int top_k, SelectSmem& sm) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int i = tid; i < top_k; i += nthr) sm.win[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += nthr) {
+    const u64 key = keys[i];
+    if (key == 0) continue;
+    int rank = 0;
+    for (int j = 0; j < n; ++j) rank += keys[j] > key;
+    if (rank < top_k) sm.win[rank] = key;
+  }
+  __syncthreads();
+}
+constexpr int RANK_SELECT_MAX = 512;      // above this the radix select wins
+
 }  // namespace mmf

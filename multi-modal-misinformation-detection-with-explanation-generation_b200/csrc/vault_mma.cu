@@ -852,9 +852,37 @@ __device__ __forceinline__ void gather_slots(const MmaParams& p, int n_pairs, in
   *n_slots = n;
 }
 
+// The same, one pair per thread (FAST tails): thread 0's serial loop over the pairs -- two 64-bit divisions
+// per pair -- was the longest single piece of the merge / rerank kernels.  *n_slots must be 0 (and a barrier
+// passed) on entry; may end up > MERGE_MAX_SLOTS, only the first MERGE_MAX_SLOTS entries are written.  The
+// order of the slots depends on the schedule of the atomics; the selection that follows does not.
+__device__ __forceinline__ void gather_slots_par(const MmaParams& p, int n_pairs, int tp, int* slots, int* n_slots) {
+  for (int c = threadIdx.x; c < n_pairs; c += blockDim.x) {
+    const PairSchedule sc = pair_schedule(p, c, n_pairs);
+    if (sc.n_tiles <= 0) continue;
+    bool touches;
+    if (c < p.n_aligned) {
+      touches = sc.tp0 == tp;
+    } else {
+      const int vl = sc.v_hi - sc.v_lo;
+      const long long first = (long long)sc.tp0 * vl + (sc.vt0 - sc.v_lo), last = first + sc.n_tiles - 1;
+      touches = vl > 0 && first / vl <= tp && tp <= last / vl;
+    }
+    if (touches) {
+      const int pos = atomicAdd(n_slots, 2);
+      if (pos + 2 <= MERGE_MAX_SLOTS) {
+        slots[pos] = (sc.sid_base + tp) * 2;
+        slots[pos + 1] = (sc.sid_base + tp) * 2 + 1;
+      }
+    }
+  }
+}
+
 // One block per query: gather the strips that cover its query tile, select + sort the top-k.
 // GUARD: runs only when the screened search flagged an overflow (*p.ovf != 0).
-template <int KPL, int CG, bool GUARD = false>
+// FAST (experimental, env MMF_MERGE_FAST=1): parallel slot gather; stage once, then rank-by-counting when few
+// candidates were staged (the usual case for small top_k) instead of 8 radix passes + a bitonic sort.
+template <int KPL, int CG, bool GUARD = false, bool FAST = false>
 __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
                                                         float* out_scores, long long* out_rows, u64* out_packed,
                                                         float* out_disc) {
@@ -867,18 +895,42 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
   const int tp = qt / CG, r = qt % CG;
-  if (threadIdx.x == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
+  if (FAST) {
+    if (threadIdx.x == 0) n_slots = 0;
+    __syncthreads();
+    gather_slots_par(p, n_pairs, tp, slots, &n_slots);
+  } else {
+    if (threadIdx.x == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
+  }
   __syncthreads();
   // lists of this query: [strip][half][r][m][C]; slot = strip*2 + half selects a block of CG*TILE_M lists
   CandidateLists src;
   const long long base = (long long)r * TILE_M + m;
   src.lists = p.cand + base * C;
   src.counts = p.cand_cnt + base;
-  src.n_lists = n_slots;
+  src.n_lists = FAST ? min(n_slots, MERGE_MAX_SLOTS) : n_slots;
   src.k_in = C;
   src.list_stride = (long long)CG * TILE_M * C;
   src.count_stride = CG * TILE_M;
   src.slots = slots;
+  if (FAST) {
+    float* os = out_scores ? out_scores + (long long)qg * p.top_k : nullptr;
+    long long* orow = out_rows ? out_rows + (long long)qg * p.top_k : nullptr;
+    u64* op = out_packed ? out_packed + (long long)qg * p.top_k : nullptr;
+    float* od = out_disc ? out_disc + qg : nullptr;
+    const u32 n = stage_candidates(src, sel, staging, 4096, (u64)p.g_tau[qg] << 32);
+    if (n <= (u32)RANK_SELECT_MAX) {
+      block_rank_select(staging, (int)n, p.top_k, sel);
+      write_topk_outputs(sel, p.top_k, os, orow, op, od, threshold);
+    } else if (n <= 4096u) {          // staged: radix select over the staged keys, read in place
+      CandidateLists ex;
+      ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n; ex.list_stride = 0; ex.count_stride = 0;
+      block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, os, orow, op, od, threshold);
+    } else {                          // does not fit: the general path re-reads global memory
+      block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, os, orow, op, od, threshold);
+    }
+    return;
+  }
   block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32,
                     out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
@@ -897,7 +949,7 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
 // Why this is the exact top-k: |approx - exact| <= eps = margin / 2 for every row.  k rows have approx >= T,
 // hence exact >= T - eps, so the exact k-th best is >= T - eps, and a row of the exact top-k has
 // approx >= T - 2 eps -- it is among the re-scored ones.
-template <int KPL, int CG>
+template <int KPL, int CG, bool FAST = false>
 __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int n_pairs, double threshold,
                                                          const uint4* __restrict__ vault, float* out_scores,
                                                          long long* out_rows, u64* out_packed, float* out_disc) {
@@ -911,13 +963,19 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   const int qt = qg / TILE_M, m = qg % TILE_M;
   const int tp = qt / CG, r = qt % CG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
+  if (FAST) {
+    if (tid == 0) n_slots = 0;
+    __syncthreads();
+    gather_slots_par(p, n_pairs, tp, slots, &n_slots);
+  } else {
+    if (tid == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
+  }
   __syncthreads();
   CandidateLists src;
   const long long base = (long long)r * TILE_M + m;
   src.lists = p.cand + base * C;
   src.counts = p.cand_cnt + base;
-  src.n_lists = n_slots;
+  src.n_lists = FAST ? min(n_slots, MERGE_MAX_SLOTS) : n_slots;
   src.k_in = C;
   src.list_stride = (long long)CG * TILE_M * C;
   src.count_stride = CG * TILE_M;
@@ -925,11 +983,28 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   // g_tau bounds the k-th best APPROXIMATE score from below; candidates down to margin below it may matter
   const u32 g = p.g_tau[qg];
   const u64 min_key = g ? (u64)okey(okey_inv(g) - p.margin) << 32 : 0ull;
-  block_select_topk(src, p.top_k, sel, staging, STAGING, min_key, nullptr, nullptr, nullptr, nullptr, threshold);
-  const u32 n_staged = sel.n_staged;
+  u32 n_staged;
+  if (FAST) {
+    n_staged = stage_candidates(src, sel, staging, STAGING, min_key);
+  } else {
+    block_select_topk(src, p.top_k, sel, staging, STAGING, min_key, nullptr, nullptr, nullptr, nullptr, threshold);
+    n_staged = sel.n_staged;
+  }
   if (n_staged > (u32)STAGING || n_slots >= MERGE_MAX_SLOTS) {   // band too wide to stage: exact redo of the batch
     if (tid == 0) *p.ovf = 1;
     return;
+  }
+  CandidateLists ex;                                             // the staged keys as one list, read in place
+  ex.lists = staging;
+  ex.counts = nullptr;
+  ex.n_lists = 1;
+  ex.k_in = (int)n_staged;
+  ex.list_stride = 0;
+  ex.count_stride = 0;
+  const bool by_rank = FAST && n_staged <= (u32)RANK_SELECT_MAX;
+  if (FAST) {                                                    // approximate top-k of the staged candidates
+    if (by_rank) block_rank_select(staging, (int)n_staged, p.top_k, sel);
+    else block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, threshold);
   }
   const u64 kth = sel.win[p.top_k - 1];                          // 0: fewer than top_k candidates -> keep all
   const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - p.margin) << 32 : 0ull;
@@ -972,13 +1047,14 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   }
   __syncthreads();
   // select + sort the exact keys: one list in shared memory (staging_cap 0: the passes read it in place)
-  CandidateLists ex;
-  ex.lists = staging;
-  ex.counts = nullptr;
-  ex.n_lists = 1;
-  ex.k_in = (int)n_staged;
-  ex.list_stride = 0;
-  ex.count_stride = 0;
+  if (by_rank) {
+    block_rank_select(staging, (int)n_staged, p.top_k, sel);
+    write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+                       out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
+                       out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
+                       threshold);
+    return;
+  }
   block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
@@ -1168,15 +1244,26 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   cfg.numAttrs = 1;
   MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
   h->launches++;
-  if constexpr ((VAR & VAR_SCREEN) != 0)
-    mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
-                                                             (long long*)out_rows, (u64*)out_packed, out_disc);
-  else if constexpr ((VAR & VAR_GUARD) != 0)
+  bool fast = false;                // experimental tails (round 2 A/B)
+  { const char* e = getenv("MMF_MERGE_FAST"); fast = e && atoi(e) != 0; }
+  if constexpr ((VAR & VAR_SCREEN) != 0) {
+    if (fast)
+      mma_rerank_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                                     (long long*)out_rows, (u64*)out_packed, out_disc);
+    else
+      mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                               (long long*)out_rows, (u64*)out_packed, out_disc);
+  } else if constexpr ((VAR & VAR_GUARD) != 0) {
     mma_merge_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
                                                                   (u64*)out_packed, out_disc);
-  else
-    mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
-                                                            (u64*)out_packed, out_disc);
+  } else {
+    if (fast)
+      mma_merge_kernel<KPL, CG, false, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores,
+                                                                          (long long*)out_rows, (u64*)out_packed, out_disc);
+    else
+      mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                              (u64*)out_packed, out_disc);
+  }
   MMF_LAUNCH_OK(h);
   return MMF_OK;
 }

@@ -178,6 +178,14 @@ int main(int argc, char** argv) {
     Result screen = search(nq, k, MMF_ALGO_MMA, &ms_screen, 20);
     setenv("MMF_MMA_SCREEN", "0", 1);
     fails += !same(screen, stream, nq, k, "screened search vs streaming kernel");
+    float ms_fast = 0;
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    setenv("MMF_MERGE_FAST", "1", 1);
+    Result fast = search(nq, k, MMF_ALGO_MMA, &ms_fast, 20);
+    unsetenv("MMF_MERGE_FAST");
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    fails += !same(fast, stream, nq, k, "screened search + fast tail vs streaming kernel");
+    printf("  search time with MMF_MERGE_FAST=1: %.3f ms (%.0f GB/s algorithmic)\n", ms_fast, rows_fp32 * 2048.0 / ms_fast * 1e-6);
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
     // band overflow: 3000 identical rows -> guarded 3-pass redo, ties by row id
@@ -213,6 +221,14 @@ int main(int argc, char** argv) {
     Result hist = search(nq, k, MMF_ALGO_MMA, &ms_hist, 10);
     unsetenv("MMF_MMA_BOUND");
     fails += !same(hist, pool, nq, k, "histogram bound vs bucket pool");
+    float ms_fast = 0;
+    setenv("MMF_MMA_BOUND", "hist", 1);
+    setenv("MMF_MERGE_FAST", "1", 1);
+    Result fast = search(nq, k, MMF_ALGO_MMA, &ms_fast, 10);
+    unsetenv("MMF_MERGE_FAST");
+    unsetenv("MMF_MMA_BOUND");
+    fails += !same(fast, pool, nq, k, "histogram bound + fast merge vs bucket pool");
+    printf("  search time with MMF_MERGE_FAST=1: %.3f ms\n", ms_fast);
     const double fl = 2.0 * nq * rows_bf16 * 512;
     printf("  search time: bucket pool %.3f ms (%.0f TFLOP/s), histogram %.3f ms (%.0f TFLOP/s)\n", ms_pool,
            fl / ms_pool * 1e-9, ms_hist, fl / ms_hist * 1e-9);
@@ -242,6 +258,12 @@ int main(int argc, char** argv) {
         setenv("MMF_MMA_BOUND", "hist", 1);
         Result var = search(sh.nq, sh.k, MMF_ALGO_MMA);
         snprintf(what, sizeof what, "%s N=%lld Q=%d k=%d off=%lld", mode ? "bf16" : "fp32", sh.n, sh.nq, sh.k, sh.off);
+        setenv("MMF_MERGE_FAST", "1", 1);
+        Result fast = search(sh.nq, sh.k, MMF_ALGO_MMA);
+        unsetenv("MMF_MERGE_FAST");
+        char what_fast[112];
+        snprintf(what_fast, sizeof what_fast, "   + MMF_MERGE_FAST=1");
+        fails += !same(fast, var, sh.nq, sh.k, what_fast);
         if (mode == 0 && sh.k <= 16) {
           Result stream = search(sh.nq, sh.k, MMF_ALGO_STREAM);
           fails += !same(var, stream, sh.nq, sh.k, what);
