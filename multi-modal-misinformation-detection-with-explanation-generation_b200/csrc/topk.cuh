@@ -301,7 +301,7 @@ __device__ __forceinline__ void block_select_topk(const CandidateLists& src, int
 }
 
 
-// ---- fast tail (experimental, env MMF_MERGE_FAST=1; see mma_merge_kernel<.., FAST>) ---------------------
+// ---- fast tail (mma_merge_kernel / mma_rerank_kernel <.., FAST>; MMF_MERGE_FAST=0 selects the first form) ----
 // The three steps of block_select_topk as separate pieces, so that a kernel can stage once and pick the
 // cheapest selection for what was staged.
 

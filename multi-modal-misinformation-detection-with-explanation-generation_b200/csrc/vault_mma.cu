@@ -880,7 +880,7 @@ __device__ __forceinline__ void gather_slots_par(const MmaParams& p, int n_pairs
 
 // One block per query: gather the strips that cover its query tile, select + sort the top-k.
 // GUARD: runs only when the screened search flagged an overflow (*p.ovf != 0).
-// FAST (experimental, env MMF_MERGE_FAST=1): parallel slot gather; stage once, then rank-by-counting when few
+// FAST (default; MMF_MERGE_FAST=0 = the first form): parallel slot gather; stage once, then rank-by-counting when few
 // candidates were staged (the usual case for small top_k) instead of 8 radix passes + a bitonic sort.
 template <int KPL, int CG, bool GUARD = false, bool FAST = false>
 __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
@@ -1244,8 +1244,8 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   cfg.numAttrs = 1;
   MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
   h->launches++;
-  bool fast = false;                // experimental tails (round 2 A/B)
-  { const char* e = getenv("MMF_MERGE_FAST"); fast = e && atoi(e) != 0; }
+  bool fast = true;                 // MMF_MERGE_FAST=0 selects the first form of the tails (A/B, triage)
+  { const char* e = getenv("MMF_MERGE_FAST"); if (e && atoi(e) == 0) fast = false; }
   if constexpr ((VAR & VAR_SCREEN) != 0) {
     if (fast)
       mma_rerank_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,

@@ -135,6 +135,7 @@ int main(int argc, char** argv) {
   const long long rows_bf16_b = argc > 3 ? atoll(argv[3]) : 0;      // optional second bf16 size (e.g. 10000000)
   int fails = 0;
   printf("%s\n", mmf_version());
+  setenv("MMF_MERGE_FAST", "0", 1);        // every arm below names its switches explicitly
   { int rc = mmf_create(0, &H); if (rc != MMF_OK) { printf("mmf_create failed: %s\n", mmf_status_string(rc)); return 1; } }
   const int NQ = 4096;
   CK(cudaMalloc(&d_q, (size_t)NQ * 512 * 4));
@@ -146,7 +147,8 @@ int main(int argc, char** argv) {
   if (rows_bf16_b > rows_max) rows_max = rows_bf16_b;
   CK(cudaMalloc(&d_vault, (size_t)rows_max * 512 * 4));
 
-  if (argc > 1 && !strcmp(argv[1], "profile")) {     // one launch of each flagship kernel, for ncu
+  if (argc > 1 && !strcmp(argv[1], "profile")) {     // one launch of each flagship kernel (library defaults), for ncu
+    unsetenv("MMF_MERGE_FAST");
     fill_rows<<<(unsigned)((1000000ll * 512 + 255) / 256), 256>>>(d_vault, 1000000, 11);
     fill_rows<<<(4096 * 512 + 255) / 256, 256>>>(d_q, 4096, 12);
     CK(cudaDeviceSynchronize());
@@ -182,7 +184,7 @@ int main(int argc, char** argv) {
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
     Result fast = search(nq, k, MMF_ALGO_MMA, &ms_fast, 20);
-    unsetenv("MMF_MERGE_FAST");
+    setenv("MMF_MERGE_FAST", "0", 1);
     setenv("MMF_MMA_SCREEN", "0", 1);
     fails += !same(fast, stream, nq, k, "screened search + fast tail vs streaming kernel");
     printf("  search time with MMF_MERGE_FAST=1: %.3f ms (%.0f GB/s algorithmic)\n", ms_fast, rows_fp32 * 2048.0 / ms_fast * 1e-6);
@@ -225,7 +227,7 @@ int main(int argc, char** argv) {
     setenv("MMF_MMA_BOUND", "hist", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
     Result fast = search(nq, k, MMF_ALGO_MMA, &ms_fast, 10);
-    unsetenv("MMF_MERGE_FAST");
+    setenv("MMF_MERGE_FAST", "0", 1);
     unsetenv("MMF_MMA_BOUND");
     fails += !same(fast, pool, nq, k, "histogram bound + fast merge vs bucket pool");
     printf("  search time with MMF_MERGE_FAST=1: %.3f ms\n", ms_fast);
@@ -260,7 +262,7 @@ int main(int argc, char** argv) {
         snprintf(what, sizeof what, "%s N=%lld Q=%d k=%d off=%lld", mode ? "bf16" : "fp32", sh.n, sh.nq, sh.k, sh.off);
         setenv("MMF_MERGE_FAST", "1", 1);
         Result fast = search(sh.nq, sh.k, MMF_ALGO_MMA);
-        unsetenv("MMF_MERGE_FAST");
+        setenv("MMF_MERGE_FAST", "0", 1);
         char what_fast[112];
         snprintf(what_fast, sizeof what_fast, "   + MMF_MERGE_FAST=1");
         fails += !same(fast, var, sh.nq, sh.k, what_fast);
@@ -275,6 +277,7 @@ int main(int argc, char** argv) {
     }
     unsetenv("MMF_MMA_SCREEN");
     unsetenv("MMF_MMA_BOUND");
+    unsetenv("MMF_MERGE_FAST");
   }
   printf("launches: %lld; %s\n", (long long)mmf_launch_count(H), fails ? "SELFTEST FAILED" : "selftest ok");
   mmf_destroy(H);
