@@ -395,7 +395,8 @@ def main():
             "dtype": "bf16" if mode == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "queries_per_step": queries_per_step, "vault_rows_total": total_rows,
                        "vault_rows_per_gpu": n_local, "dim": 512, "top_k": K, "vault_mode": mode, "algo": args.algo,
-                       "parallelism": ("vault row-sharded x%d + NCCL all-gather merge" % world) if sharded else
+                       "parallelism": ("vault row-sharded x%d + %s" % (world, "peer-memory exchange (csrc/exchange.cu)"
+                                       if vault.exchange == "p2p" else "NCCL all-gather merge")) if sharded else
                                       ("replica x%d, queries sharded, no collective" % world),
                        "l2": f"vault shard {n_local * 512 * elem / 1e6:.0f} MB streamed per step (> 126 MB L2), no flush needed"},
             "roofline": roof, "cpu_baseline": cpu,

@@ -119,6 +119,25 @@ int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n
                    double threshold, float* out_scores, int64_t* out_rows, float* out_discrepancy,
                    mmf_stream_t stream);
 
+/* ---- Candidate exchange over NVLink peer memory (row-sharded search) ------------------
+ * Alternative to "mmf_vault_search_candidates + NCCL all-gather + mmf_topk_merge": every rank stores its
+ * candidates straight into the peers' gather buffers and the merge kernel waits on per-rank flags, so the
+ * sharded search is three launches and no library collective (csrc/exchange.cu).
+ * The buffers are SYMMETRIC MEMORY owned by the caller (e.g. torch.distributed._symmetric_memory): one
+ * allocation of bytes_per_rank on every rank, mapped into every process; peer_ptrs is a HOST array of `world`
+ * device addresses (peer_ptrs[r] = rank r's buffer as seen from this process; peer_ptrs[rank] = the local one).
+ * mmf_exchange_layout says how many bytes an exchange of (n_queries, k_in) candidates per rank needs.
+ * Protocol: all ranks attach, the caller barriers, then all ranks call mmf_vault_search_exchange the same
+ * number of times with the same (n_queries, top_k, k_local).  world <= 16.  Synchronous: attach / detach. */
+int mmf_exchange_layout(int world, int64_t n_queries, int k_in, int64_t* gather_bytes_per_parity, int64_t* bytes_needed);
+int mmf_exchange_attach(mmf_handle* h, int rank, int world, const uint64_t* peer_ptrs, int64_t bytes_per_rank);
+int mmf_exchange_detach(mmf_handle* h);
+/* Local search (k_local = min(top_k, rows per rank) candidates per query) + push + wait + merge.  Outputs as
+ * mmf_vault_search, identical on every rank; asynchronous on `stream`. */
+int mmf_vault_search_exchange(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int k_local,
+                              double threshold, int algo, float* out_scores, int64_t* out_rows,
+                              float* out_discrepancy, mmf_stream_t stream);
+
 /* ---- Fusion judge --------------------------------------------------------------------
  * Weights of MultiModalMisinfoDetector.fusion_layer (misinfo_forensics.py:83-90), in the
  * order and nn.Linear layout of the .pth (train_fusion_judge.py:259-267):

@@ -13,6 +13,7 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                    float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st);
 int mmf_mma_supported(const mmf_handle* h, int64_t n_queries, int top_k);
 void mmf_mma_destroy(mmf_handle* h);
+extern "C" int mmf_exchange_detach(mmf_handle* h);
 int mmf_fill_empty(mmf_handle* h, int64_t n_queries, int top_k, float* out_scores, int64_t* out_rows,
                    uint64_t* out_packed, float* out_disc, cudaStream_t st);
 
@@ -98,6 +99,7 @@ extern "C" int mmf_destroy(mmf_handle* h) {
   if (!h) return MMF_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  mmf_exchange_detach(h);
   mmf_mma_destroy(h);
   if (h->vault) cudaFree(h->vault);
   if (h->fusion_params) cudaFree(h->fusion_params);
@@ -148,6 +150,12 @@ static int search_dispatch(mmf_handle* h, const float* queries, int64_t n_querie
     if (rc != MMF_OK) return rc;
   }
   return MMF_OK;
+}
+
+// local search with packed output, for the peer-memory exchange (exchange.cu)
+int mmf_search_dispatch_packed(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int algo,
+                               uint64_t* out_packed, cudaStream_t st, const char* who) {
+  return search_dispatch(h, queries, n_queries, top_k, 0.0, algo, nullptr, nullptr, out_packed, nullptr, st, who);
 }
 
 extern "C" int mmf_vault_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,

@@ -93,6 +93,8 @@ struct mmf_handle {
   cudaStream_t own_stream = nullptr;
   // TMA descriptors for the tcgen05 path live in vault_mma.cu's state
   void* mma_state = nullptr;
+  // peer-memory candidate exchange (exchange.cu), null until mmf_exchange_attach
+  void* xchg_state = nullptr;
 };
 
 int mmf_set_error(mmf_handle* h, int status, const char* fmt, ...);

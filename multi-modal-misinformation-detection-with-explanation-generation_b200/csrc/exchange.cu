@@ -1,0 +1,227 @@
+// Row-sharded Truth-Vault search: the candidate exchange over NVLink peer memory.
+//
+// Every rank searches its own row shard and ends up with its local top-k per query as packed candidates
+// ((order-preserving score key << 32) | global row id, topk.cuh).  The global result is the top-k of the
+// union, so the ranks must see each other's candidates: 8 B x top_k x queries per rank (C4: 3.3 MB).
+// The first implementation all-gathers them with NCCL (vault.py: exchange_candidates) and merges in a
+// second kernel.  This file does the same exchange with plain stores into the peers' memory:
+//
+//   exchange_push_kernel     every rank WRITES its candidates straight into slot [rank] of every peer's
+//                            gather buffer (symmetric memory mapped into this process: ordinary global
+//                            stores that travel over NVLink / NVSwitch), then the last block to finish
+//                            publishes the epoch in flag [rank] of every peer (st.release.sys);
+//   exchange_wait_merge_kernel
+//                            one block per query: waits (ld.acquire.sys) until all `world` flags of THIS
+//                            rank carry the epoch, then selects + sorts the global top-k from the `world`
+//                            lists (block_select_topk, the discrepancy rule fused) -- the merge starts the
+//                            moment the last peer's candidates land, with no host round trip, no NCCL
+//                            kernel and no intermediate copy.
+//
+// Buffer of one rank (identical layout on all ranks; `bytes_per_rank` as attached):
+//   [0, 1024)            flags: u32 flag[2][MMF_XCHG_MAX_WORLD], flag[parity][src] = epoch of the last exchange
+//                        whose candidates from rank `src` are complete in gather[parity]
+//   [1024, ...)          gather[2][world][n_queries][top_k] u64 (laid out per call; both parities must fit)
+// Two parities (epoch & 1): a peer may already push exchange e+1 while this rank still merges exchange e.
+// It cannot get to e+2 before this rank has pushed e+1 -- which this rank does after its merge of e, in stream
+// order -- so two buffers are enough and no back-signal is needed.
+//
+// Progress: a push never waits, and every rank enqueues its push before its wait-merge, so the spinning
+// blocks of the wait-merge kernel cannot keep a needed kernel off the device.
+//
+// STATUS: compiles for sm_100a; NOT yet run on a multi-GPU box (written after the round's GPU time was spent).
+// Off by default: TruthVault(exchange="p2p") / MMF_EXCHANGE=p2p selects it, the NCCL all-gather stays the default.
+#include "common.cuh"
+#include "topk.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#define MMF_XCHG_MAX_WORLD 16
+#define MMF_XCHG_HEADER 1024
+
+int mmf_search_dispatch_packed(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int algo,
+                               uint64_t* out_packed, cudaStream_t st, const char* who);
+
+namespace mmf {
+
+struct ExchangePeers {
+  unsigned char* base[MMF_XCHG_MAX_WORLD];     // peer r's buffer as mapped in this process
+};
+
+struct ExchangeState {
+  int rank = 0, world = 0;
+  size_t bytes_per_rank = 0;
+  ExchangePeers peers;
+  u32 epoch = 0;                                // exchanges done so far (all ranks call in the same order)
+  u64* local = nullptr;                         // this rank's packed candidates of the current call
+  size_t local_bytes = 0;
+  u32* done = nullptr;                          // ticket counter of the push kernel (device, self-resetting)
+};
+
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
+  u32 v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// n = n_queries * top_k keys of this rank -> slot [rank] of gather[parity] on every rank (own copy included,
+// so that the merge reads one layout).  Stores to one peer are contiguous: 8 B per thread, coalesced.
+__global__ void __launch_bounds__(256) exchange_push_kernel(const u64* __restrict__ local, long long n, ExchangePeers peers,
+                                                            int rank, int world, size_t slot_off, int parity, u32 epoch,
+                                                            u32* done) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const u64 key = local[i];
+#pragma unroll 1
+    for (int r = 0; r < world; ++r) {
+      const int peer = (rank + r) % world;                     // start with the own copy, spread the links
+      reinterpret_cast<u64*>(peers.base[peer] + slot_off)[i] = key;
+    }
+  }
+  __threadfence_system();                                      // this thread's peer stores, system scope
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) {
+    const u32 ticket = atomicAdd(done, 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  // every block's stores are ordered before its ticket (fence + barrier + atomic); the last block publishes
+  if (threadIdx.x == 0) *done = 0;                             // self-reset for the next exchange
+  __threadfence_system();
+  if ((int)threadIdx.x < world) {
+    u32* flag = reinterpret_cast<u32*>(peers.base[threadIdx.x]) + parity * MMF_XCHG_MAX_WORLD + rank;
+    st_release_sys(flag, epoch);
+  }
+}
+
+// One block per query: wait for all ranks' candidates of this epoch, then merge the `world` lists.
+__global__ void __launch_bounds__(256) exchange_wait_merge_kernel(const unsigned char* own, int world,
+                                                                  size_t gather_off, int parity, u32 epoch,
+                                                                  long long n_queries, int k_in, int top_k,
+                                                                  double threshold, float* out_scores,
+                                                                  long long* out_rows, float* out_disc) {
+  __shared__ SelectSmem sel;
+  __shared__ u64 staging[4096];
+  if ((int)threadIdx.x < world) {
+    const u32* flag = reinterpret_cast<const u32*>(own) + parity * MMF_XCHG_MAX_WORLD + threadIdx.x;
+    // epochs only grow; (int) difference tolerates the 32-bit wrap
+    while ((int)(ld_acquire_sys(flag) - epoch) < 0) __nanosleep(64);
+  }
+  __syncthreads();
+  const long long qg = blockIdx.x;
+  CandidateLists src;
+  src.lists = reinterpret_cast<const u64*>(own + gather_off) + qg * k_in;
+  src.counts = nullptr;
+  src.n_lists = world;
+  src.k_in = k_in;
+  src.list_stride = n_queries * k_in;
+  src.count_stride = 0;
+  block_select_topk(src, top_k, sel, staging, 4096, 0ull, out_scores ? out_scores + qg * top_k : nullptr,
+                    out_rows ? out_rows + qg * top_k : nullptr, nullptr, out_disc ? out_disc + qg : nullptr, threshold);
+}
+
+}  // namespace mmf
+
+using namespace mmf;
+
+// Byte offsets inside a rank's buffer for an exchange of (n_queries, k_in) candidates per rank.
+// Host-only, also exported for the CPU test-suite.
+extern "C" int mmf_exchange_layout(int world, int64_t n_queries, int k_in, int64_t* gather_bytes_per_parity,
+                                   int64_t* bytes_needed) {
+  if (world < 1 || world > MMF_XCHG_MAX_WORLD || n_queries < 0 || k_in < 1) return MMF_ERR_BAD_ARG;
+  const int64_t per_parity = (((int64_t)world * n_queries * k_in * 8) + 1023) / 1024 * 1024;
+  if (gather_bytes_per_parity) *gather_bytes_per_parity = per_parity;
+  if (bytes_needed) *bytes_needed = MMF_XCHG_HEADER + 2 * per_parity;
+  return MMF_OK;
+}
+
+extern "C" int mmf_exchange_attach(mmf_handle* h, int rank, int world, const uint64_t* peer_ptrs, int64_t bytes_per_rank) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (world < 1 || world > MMF_XCHG_MAX_WORLD || rank < 0 || rank >= world || !peer_ptrs || bytes_per_rank < MMF_XCHG_HEADER)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "exchange_attach: bad argument (rank=%d world=%d bytes=%lld)", rank, world,
+                         (long long)bytes_per_rank);
+  for (int r = 0; r < world; ++r)
+    if (!peer_ptrs[r]) return mmf_set_error(h, MMF_ERR_BAD_ARG, "exchange_attach: null pointer for rank %d", r);
+  MMF_CUDA_OK(h, cudaSetDevice(h->device));
+  ExchangeState* x = (ExchangeState*)h->xchg_state;
+  if (!x) {
+    x = new (std::nothrow) ExchangeState();
+    if (!x) return mmf_set_error(h, MMF_ERR_NOMEM, "exchange_attach: out of host memory");
+    h->xchg_state = x;
+    MMF_CUDA_OK(h, cudaMalloc(&x->done, 256));
+    MMF_CUDA_OK(h, cudaMemset(x->done, 0, 256));
+  }
+  x->rank = rank;
+  x->world = world;
+  x->bytes_per_rank = (size_t)bytes_per_rank;
+  x->epoch = 0;
+  memset(&x->peers, 0, sizeof x->peers);
+  for (int r = 0; r < world; ++r) x->peers.base[r] = reinterpret_cast<unsigned char*>((uintptr_t)peer_ptrs[r]);
+  // the flags of THIS rank start at 0 (= no exchange seen); the caller barriers after attaching
+  MMF_CUDA_OK(h, cudaMemset(x->peers.base[rank], 0, MMF_XCHG_HEADER));
+  MMF_CUDA_OK(h, cudaDeviceSynchronize());
+  return MMF_OK;
+}
+
+extern "C" int mmf_exchange_detach(mmf_handle* h) {
+  if (!h || !h->xchg_state) return MMF_OK;
+  ExchangeState* x = (ExchangeState*)h->xchg_state;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  if (x->local) cudaFree(x->local);
+  if (x->done) cudaFree(x->done);
+  delete x;
+  h->xchg_state = nullptr;
+  return MMF_OK;
+}
+
+extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int k_local,
+                                         double threshold, int algo, float* out_scores, int64_t* out_rows,
+                                         float* out_discrepancy, mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  ExchangeState* x = (ExchangeState*)h->xchg_state;
+  if (!x) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_search_exchange: no peer buffers attached");
+  if (n_queries < 0 || top_k < 1 || top_k > MMF_MAX_TOP_K || k_local < 1 || k_local > top_k ||
+      (n_queries > 0 && (!queries || !out_scores || !out_rows)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_exchange: bad argument (n_queries=%lld top_k=%d k_local=%d)",
+                         (long long)n_queries, top_k, k_local);
+  if (n_queries == 0) return MMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t per_parity = 0, need = 0;
+  mmf_exchange_layout(x->world, n_queries, k_local, &per_parity, &need);
+  if ((size_t)need > x->bytes_per_rank)
+    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: %lld bytes of peer buffer needed, %zu attached",
+                         (long long)need, x->bytes_per_rank);
+  const size_t local_bytes = (size_t)n_queries * k_local * 8;
+  if (local_bytes > x->local_bytes) {
+    MMF_CUDA_OK(h, cudaDeviceSynchronize());
+    if (x->local) MMF_CUDA_OK(h, cudaFree(x->local));
+    x->local = nullptr;
+    x->local_bytes = 0;
+    MMF_CUDA_OK(h, cudaMalloc(&x->local, local_bytes));
+    x->local_bytes = local_bytes;
+  }
+  // 1. local search of this rank's shard -> packed candidates with GLOBAL row ids
+  int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)x->local, st, "vault_search_exchange");
+  if (rc != MMF_OK) return rc;
+  // 2. push into every rank's gather buffer + publish, 3. wait for everybody's + merge
+  const u32 epoch = ++x->epoch;
+  const int parity = (int)(epoch & 1u);
+  const size_t gather_off = MMF_XCHG_HEADER + (size_t)parity * (size_t)per_parity;
+  const size_t slot_off = gather_off + (size_t)x->rank * local_bytes;
+  const long long n = (long long)n_queries * k_local;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+  exchange_push_kernel<<<blocks, 256, 0, st>>>(x->local, n, x->peers, x->rank, x->world, slot_off, parity, epoch, x->done);
+  MMF_LAUNCH_OK(h);
+  exchange_wait_merge_kernel<<<(unsigned)n_queries, 256, 0, st>>>(x->peers.base[x->rank], x->world, gather_off, parity, epoch,
+                                                                 (long long)n_queries, k_local, top_k, threshold, out_scores,
+                                                                 (long long*)out_rows, out_discrepancy);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}

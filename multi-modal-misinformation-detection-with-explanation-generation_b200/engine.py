@@ -166,6 +166,34 @@ class Engine:
                                             _ptr(scores), _ptr(rows), _ptr(disc), self._stream()))
         return scores, rows, disc
 
+    # ------------------------------------------------------------------ peer-memory candidate exchange
+    def exchange_layout(self, world: int, n_queries: int, k_in: int) -> int:
+        """Bytes of symmetric memory per rank that an exchange of (n_queries, k_in) candidates needs."""
+        need = C.c_int64()
+        self._check(self.lib.mmf_exchange_layout(int(world), int(n_queries), int(k_in), None, C.byref(need)))
+        return int(need.value)
+
+    def exchange_attach(self, rank: int, world: int, peer_ptrs, bytes_per_rank: int) -> None:
+        """peer_ptrs[r]: device address of rank r's symmetric buffer as mapped in this process."""
+        arr = (C.c_uint64 * int(world))(*[int(x) for x in peer_ptrs])
+        self._check(self.lib.mmf_exchange_attach(self._h, int(rank), int(world), arr, int(bytes_per_rank)))
+
+    def exchange_detach(self) -> None:
+        self._check(self.lib.mmf_exchange_detach(self._h))
+
+    def vault_search_exchange(self, queries, top_k: int, k_local: int, threshold: float = VAULT_THRESHOLD,
+                              algo: str = "auto") -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Row-sharded search with the candidate exchange over NVLink peer memory (csrc/exchange.cu): local
+        search + push into the peers' buffers + wait + merge, no NCCL call.  Outputs as vault_search."""
+        q = self._dev_f32(queries, 512)
+        nq = q.shape[0]
+        scores = torch.empty((nq, top_k), dtype=torch.float32, device=self.device)
+        rows = torch.empty((nq, top_k), dtype=torch.int64, device=self.device)
+        disc = torch.empty(nq, dtype=torch.float32, device=self.device)
+        self._check(self.lib.mmf_vault_search_exchange(self._h, _ptr(q), nq, int(top_k), int(k_local), float(threshold),
+                                                       _ALGO[algo], _ptr(scores), _ptr(rows), _ptr(disc), self._stream()))
+        return scores, rows, disc
+
     # ------------------------------------------------------------------ fusion judge
     def fusion_load(self, state_dict) -> None:
         """state_dict with keys 0.weight,0.bias,3.weight,3.bias,5.weight,5.bias (optionally under

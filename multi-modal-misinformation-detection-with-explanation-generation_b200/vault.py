@@ -4,6 +4,7 @@ returns the reference's `matches` records.  Strings (titles/urls) stay on the ho
 indexed by global row id; only (row id, score) comes back from the device."""
 from __future__ import annotations
 
+import os
 import pickle
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
@@ -73,8 +74,16 @@ class TruthVault:
     """A (possibly row-sharded) vault resident in HBM plus its host-side metadata."""
 
     def __init__(self, engine: Engine, embeddings, metadata: Optional[Sequence[dict]] = None, mode: str = "fp32",
-                 rank: int = 0, world: int = 1, group=None, n_total: Optional[int] = None, row_offset: Optional[int] = None):
+                 rank: int = 0, world: int = 1, group=None, n_total: Optional[int] = None, row_offset: Optional[int] = None,
+                 exchange: Optional[str] = None):
+        """exchange: how the shards' candidates meet when world > 1 -- "nccl" (one all-gather, the default) or
+        "p2p" (stores into the peers' symmetric memory + flag wait fused into the merge kernel, csrc/exchange.cu;
+        not yet validated on a multi-GPU box); None reads MMF_EXCHANGE."""
         self.engine = engine
+        self.exchange = (exchange or os.environ.get("MMF_EXCHANGE", "nccl")).lower()
+        if self.exchange not in ("nccl", "p2p"):
+            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {self.exchange!r}")
+        self._symm = None          # (tensor, handle, bytes) of the symmetric exchange buffer
         self.metadata = metadata
         self.mode = mode
         self.rank, self.world, self.group = rank, world, group
@@ -98,9 +107,34 @@ class TruthVault:
         if self.world == 1:
             return self.engine.vault_search(queries, top_k, threshold, algo)
         k_local = min(top_k, max(1, self.plan.rows_per_rank))
+        if self.exchange == "p2p":
+            nq = int(queries.shape[0]) if hasattr(queries, "shape") and len(queries.shape) == 2 else 1
+            self._ensure_peer_buffers(nq, k_local)
+            return self.engine.vault_search_exchange(queries, top_k, k_local, threshold, algo)
         packed = self.engine.vault_search_candidates(queries, k_local, algo)
         gathered = exchange_candidates(packed, self.group)
         return self.engine.topk_merge(gathered, top_k, threshold)
+
+    def _ensure_peer_buffers(self, n_queries: int, k_local: int) -> None:
+        """(Re)allocate the symmetric exchange buffer when this search needs more than is attached.  Collective:
+        every rank runs the same searches in the same order, so all of them get here together."""
+        need = self.engine.exchange_layout(self.world, n_queries, k_local)
+        if self._symm is not None and self._symm[2] >= need:
+            return
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if self._symm is not None:
+            torch.cuda.synchronize(self.engine.device)
+            dist.barrier(self.group)                  # nobody still pushes into the buffers being replaced
+            self.engine.exchange_detach()
+        nbytes = max(need + need // 2, 1 << 20)
+        buf = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=self.engine.device)
+        group = self.group if self.group is not None else dist.group.WORLD
+        hdl = symm_mem.rendezvous(buf, group)
+        self.engine.exchange_attach(self.rank, self.world, list(hdl.buffer_ptrs), (nbytes // 8) * 8)
+        torch.cuda.synchronize(self.engine.device)
+        dist.barrier(self.group)                      # every rank has cleared its flags before anyone pushes
+        self._symm = (buf, hdl, (nbytes // 8) * 8)
 
     def matches(self, scores_row, rows_row) -> List[dict]:
         """The reference's match records (misinfo_forensics.py:452-460) for one query."""

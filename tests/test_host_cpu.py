@@ -194,3 +194,20 @@ def test_mma_histogram_bound_is_valid_and_tight():
     assert bound(np.array([2.0 ** -7] * 4 + [2.0 ** -8], np.float32), 4) == -np.inf   # bin 0 carries no bound
     assert bound(np.array([2.0 ** -7 * (1 + 1 / 32)] * 4, np.float32), 4) == np.float32(2.0 ** -7 * (1 + 1 / 32))
     assert lib.mmf_mma_hist_bound(None, 0, 5, None) == -1
+
+
+def test_exchange_layout_and_argument_checks():
+    """peer-memory candidate exchange (csrc/exchange.cu): buffer sizing is host logic; the device side needs >= 1 GPU"""
+    import ctypes as C
+    lib = _lib.load()
+    per, need = C.c_int64(), C.c_int64()
+    assert lib.mmf_exchange_layout(8, 4096, 100, C.byref(per), C.byref(need)) == 0
+    assert per.value >= 8 * 4096 * 100 * 8 and per.value % 1024 == 0          # world x Q x k packed candidates
+    assert need.value == 1024 + 2 * per.value                                    # flag header + two parities
+    assert lib.mmf_exchange_layout(1, 0, 1, C.byref(per), C.byref(need)) == 0 and need.value == 1024
+    for bad in ((0, 1, 1), (17, 1, 1), (2, -1, 1), (2, 1, 0)):
+        assert lib.mmf_exchange_layout(*bad, None, None) == -1
+    assert lib.mmf_exchange_attach(None, 0, 1, None, 0) == -1
+    assert lib.mmf_exchange_detach(None) == 0
+    with pytest.raises(ValueError):
+        mmf_b200.TruthVault(None, np.zeros((4, 512), np.float32), exchange="carrier-pigeon")

@@ -279,6 +279,68 @@ int main(int argc, char** argv) {
     unsetenv("MMF_MMA_BOUND");
     unsetenv("MMF_MERGE_FAST");
   }
+  // ---------------- peer-memory candidate exchange (csrc/exchange.cu): 2 ranks emulated on ONE device
+  // (two handles, two streams, two buffers of this device).  Small query counts only: on one GPU the spinning
+  // wait-merge blocks of "rank 0" must leave room for the kernels of "rank 1" (on real ranks they cannot collide).
+  {
+    printf("[exchange] 2 emulated ranks vs the unsharded search\n");
+    mmf_handle* R[2] = {nullptr, nullptr};
+    cudaStream_t S[2];
+    for (int r = 0; r < 2; ++r) {
+      if (mmf_create(0, &R[r]) != MMF_OK) { printf("mmf_create failed\n"); return 1; }
+      CK(cudaStreamCreateWithFlags(&S[r], cudaStreamNonBlocking));
+    }
+    const long long n = 200001;
+    const int nq = 24;
+    int64_t need = 0;
+    mmf_exchange_layout(2, nq, 100, nullptr, &need);
+    void* B[2];
+    uint64_t ptrs[2];
+    for (int r = 0; r < 2; ++r) { CK(cudaMalloc(&B[r], (size_t)need)); ptrs[r] = (uint64_t)(uintptr_t)B[r]; }
+    float* sc[2]; int64_t* ro[2]; float* di[2];
+    for (int r = 0; r < 2; ++r) {
+      CK(cudaMalloc(&sc[r], (size_t)nq * 100 * 4)); CK(cudaMalloc(&ro[r], (size_t)nq * 100 * 8)); CK(cudaMalloc(&di[r], nq * 4));
+    }
+    fill_rows<<<(unsigned)((n * 512 + 255) / 256), 256>>>(d_vault, n, 31);
+    fill_rows<<<(nq * 512 + 255) / 256, 256>>>(d_q, nq, 32);
+    plant_queries<<<(6 * 512 + 255) / 256, 256>>>(d_q, d_vault, 6, n / 6, 1.0f);
+    CK(cudaDeviceSynchronize());
+    const long long half = (n + 1) / 2;
+    for (int mode = 0; mode < 2; ++mode) {
+      const int vm = mode == 0 ? MMF_VAULT_FP32 : MMF_VAULT_BF16;
+      MM(mmf_vault_load(H, d_vault, 1, n, 512, MMF_F32, vm, 0));
+      for (int r = 0; r < 2; ++r) {
+        int rc = mmf_vault_load(R[r], d_vault + (r ? half * 512 : 0), 1, r ? n - half : half, 512, MMF_F32, vm, r ? half : 0);
+        if (rc == MMF_OK) rc = mmf_exchange_attach(R[r], r, 2, ptrs, need);
+        if (rc != MMF_OK) { printf("rank %d setup failed: %s\n", r, mmf_last_error(R[r])); return 1; }
+      }
+      const int ks[3] = {10, 100, 5};
+      for (int t = 0; t < 3; ++t) {
+        const int k = ks[t];
+        for (int algo = MMF_ALGO_STREAM; algo <= MMF_ALGO_MMA; ++algo) {
+          Result full = search(nq, k, algo);
+          for (int rep = 0; rep < 3; ++rep) {       // 3 back-to-back exchanges: both parities + buffer reuse
+            for (int r = 0; r < 2; ++r) {
+              int rc = mmf_vault_search_exchange(R[r], d_q, nq, k, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
+              if (rc != MMF_OK) { printf("search_exchange failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+            }
+          }
+          CK(cudaDeviceSynchronize());
+          for (int r = 0; r < 2; ++r) {
+            Result got;
+            got.scores.resize((size_t)nq * k); got.rows.resize((size_t)nq * k); got.disc.resize(nq);
+            CK(cudaMemcpy(got.scores.data(), sc[r], got.scores.size() * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(got.rows.data(), ro[r], got.rows.size() * 8, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(got.disc.data(), di[r], got.disc.size() * 4, cudaMemcpyDeviceToHost));
+            char what[96];
+            snprintf(what, sizeof what, "%s k=%d %s rank %d", mode ? "bf16" : "fp32", k, algo == MMF_ALGO_MMA ? "tcgen05" : "stream", r);
+            fails += !same(got, full, nq, k, what);
+          }
+        }
+      }
+    }
+    for (int r = 0; r < 2; ++r) { mmf_destroy(R[r]); cudaFree(B[r]); cudaFree(sc[r]); cudaFree(ro[r]); cudaFree(di[r]); cudaStreamDestroy(S[r]); }
+  }
   printf("launches: %lld; %s\n", (long long)mmf_launch_count(H), fails ? "SELFTEST FAILED" : "selftest ok");
   mmf_destroy(H);
   return fails ? 1 : 0;
