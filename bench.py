@@ -175,6 +175,9 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--rows", type=int, default=0, help="override vault rows (debug only; the line then says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-api", default="tensors", choices=["tensors", "host"],
+                    help="e2e leg: mmf_b200.score_batch on pinned tensors + .cpu() per result (default), or the single "
+                         "host-buffer library call Engine.score_batch_host (not yet validated on a GPU)")
     ap.add_argument("--no-verify", action="store_true", help="skip the planted-row sanity check (perf triage with MMF_MMA_DEBUG)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -249,6 +252,10 @@ def main():
         return mmf_b200.score_batch(eng, vault, text_dev, img_dev, head_dev, None, K, args.algo)
 
     def step_e2e():
+        if args.e2e_api == "host" and not sharded:
+            out = eng.score_batch_host(text_host, img_host, head_host, None, K, algo=args.algo)
+            return tuple(torch.from_numpy(out[key]) for key in ("verdict", "probs", "vault_scores", "vault_rows",
+                                                                 "clip_similarity", "vault_discrepancy", "scores", "confidence"))
         out = mmf_b200.score_batch(eng, vault, text_host, img_host, head_host, None, K, args.algo)
         return (out["verdict"].cpu(), out["probs"].cpu(), out["vault_scores"].cpu(), out["vault_rows"].cpu(),
                 out["clip_similarity"].cpu(), out["vault_discrepancy"].cpu())
@@ -401,7 +408,9 @@ def main():
                        "l2": f"vault shard {n_local * 512 * elem / 1e6:.0f} MB streamed per step (> 126 MB L2), no flush needed"},
             "roofline": roof, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "api": "mmf_b200.score_batch on pinned host tensors + .cpu() of the results"},
+                    "d2h_bytes_per_step": d2h, "api": ("Engine.score_batch_host (mmf_score_batch_host): one library call, pinned host buffers in, host arrays out"
+                            if args.e2e_api == "host" and not sharded else
+                            "mmf_b200.score_batch on pinned host tensors + .cpu() of the results")},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line))

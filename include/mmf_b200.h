@@ -160,6 +160,20 @@ int mmf_fusion_forward(mmf_handle* h, const float* x, int64_t n, float* out_prob
 int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modality, int64_t n, float* out_probs,
                       int32_t* out_verdict, float* out_confidence, mmf_stream_t stream);
 
+/* The whole path for a batch with HOST buffers in and out (the end-to-end call): H2D of the embeddings,
+ * caption/image cosine, vault search (zero discrepancy / no matches when no vault is loaded, misinfo_forensics.py:
+ * 422-428), score assembly with the skipped-modality zeros of :794-809, fusion judge / fallback verdict, one D2H,
+ * one stream synchronisation; returns when the results are in host memory.  Pinned host buffers make the copies
+ * asynchronous DMA.  text/image: (n,512) fp32; head: (n,3) fp32 = [ai, misinfo, deepfake]; modality: (n) uint8
+ * (bit0 text, bit1 visual) or NULL = both.  Outputs (any but out_probs may be NULL): clip_similarity (n),
+ * vault_discrepancy (n), vault_scores (n,top_k), vault_rows (n,top_k) int64, scores5 (n,5) = the fusion inputs,
+ * probs (n,2) [real,fake], verdict (n) int32, confidence (n).  Single-GPU / replica vaults only. */
+int mmf_score_batch_host(mmf_handle* h, const float* text_host, const float* image_host, const float* head_host,
+                         const uint8_t* modality_host, int64_t n, int top_k, double threshold, int algo,
+                         float* out_clip_similarity, float* out_vault_discrepancy, float* out_vault_scores,
+                         int64_t* out_vault_rows, float* out_scores5, float* out_probs, int32_t* out_verdict,
+                         float* out_confidence);
+
 /* Host-only self check of the tcgen05 search's work decomposition for a (n_queries, n_rows) problem on a
  * device with sm_count SMs: MMF_OK iff every (query-tile group, vault tile) unit is scheduled exactly once,
  * strip ids are unique and the load is balanced.  Needs no GPU (used by the CPU test-suite). */

@@ -217,3 +217,111 @@ extern "C" int mmf_vault_search_host(mmf_handle* h, const float* queries_host, i
   if (out_discrepancy_host) memcpy(out_discrepancy_host, hp + bq + bs + br, (size_t)n_queries * 4);
   return MMF_OK;
 }
+
+// ---- batched analyze downstream of the encoders, HOST buffers in and out ---------------------------------
+// The whole hot path for a batch in one call: H2D of the embeddings, caption/image cosine (K1), vault search
+// (K2 / K3), score assembly with the modality rules of misinfo_forensics.py:794-809, fusion judge / fallback
+// verdict (K5), ONE D2H of all results, ONE stream synchronisation.  Same results as mmf_b200.score_batch
+// (pipeline.py), which issues the same kernels from Python with one torch op and one .cpu() sync per tensor.
+namespace mmf {
+// x[i] = [ai, misinfo, deepfake, clip_sim, vault_disc] with the skipped modalities zeroed; sim / disc masked in place
+__global__ void __launch_bounds__(256) assemble_scores_kernel(const float* __restrict__ head, const unsigned char* __restrict__ mod_in,
+                                                              long long n, float* __restrict__ sim, float* __restrict__ disc,
+                                                              float* __restrict__ x, unsigned char* __restrict__ mod_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int mod = mod_in ? mod_in[i] : 3;
+  const bool has_text = mod & 1, has_vis = mod & 2;
+  const float s = (has_text && has_vis) ? sim[i] : 0.f;      // analyze() skips the steps whose modality is missing
+  const float d = has_vis ? disc[i] : 0.f;
+  sim[i] = s;
+  disc[i] = d;
+  x[i * 5 + 0] = has_text ? head[i * 3 + 0] : 0.f;
+  x[i * 5 + 1] = has_text ? head[i * 3 + 1] : 0.f;
+  x[i * 5 + 2] = has_vis ? head[i * 3 + 2] : 0.f;
+  x[i * 5 + 3] = s;
+  x[i * 5 + 4] = d;
+  mod_out[i] = (unsigned char)mod;
+}
+}  // namespace mmf
+
+extern "C" int mmf_score_batch_host(mmf_handle* h, const float* text_host, const float* image_host, const float* head_host,
+                                    const uint8_t* modality_host, int64_t n, int top_k, double threshold, int algo,
+                                    float* out_clip_similarity, float* out_vault_discrepancy, float* out_vault_scores,
+                                    int64_t* out_vault_rows, float* out_scores5, float* out_probs, int32_t* out_verdict,
+                                    float* out_confidence) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n < 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K ||
+      (n > 0 && (!text_host || !image_host || !head_host || !out_probs)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_host: bad argument (n=%lld top_k=%d)", (long long)n, top_k);
+  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "score_batch_host: fusion weights not loaded");
+  if (n == 0) return MMF_OK;
+  MMF_CUDA_OK(h, cudaSetDevice(h->device));
+  cudaStream_t st = h->own_stream;
+  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+  // device buffer: inputs, then ONE contiguous block of outputs (mirrored by the pinned staging buffer)
+  const size_t b_emb = al((size_t)n * MMF_DIM * 4), b_head = al((size_t)n * 3 * 4), b_mod = al((size_t)n);
+  const size_t o_sim = 0, o_disc = o_sim + al((size_t)n * 4), o_vs = o_disc + al((size_t)n * 4);
+  const size_t o_vr = o_vs + al((size_t)n * top_k * 4), o_x = o_vr + al((size_t)n * top_k * 8);
+  const size_t o_probs = o_x + al((size_t)n * 5 * 4), o_verdict = o_probs + al((size_t)n * 2 * 4);
+  const size_t o_conf = o_verdict + al((size_t)n * 4), out_bytes = o_conf + al((size_t)n * 4);
+  const size_t in_bytes = 2 * b_emb + b_head + 2 * b_mod;
+  const size_t total = in_bytes + out_bytes;
+  int rc = ensure_pinned(h, out_bytes);
+  if (rc != MMF_OK) return rc;
+  if (total > h->io_bytes) {
+    MMF_CUDA_OK(h, cudaStreamSynchronize(st));
+    if (h->io) MMF_CUDA_OK(h, cudaFree(h->io));
+    h->io = nullptr;
+    h->io_bytes = 0;
+    MMF_CUDA_OK(h, cudaMalloc(&h->io, total));
+    h->io_bytes = total;
+  }
+  char* dp = (char*)h->io;
+  float* d_text = (float*)dp;
+  float* d_img = (float*)(dp + b_emb);
+  float* d_head = (float*)(dp + 2 * b_emb);
+  unsigned char* d_mod_in = (unsigned char*)(dp + 2 * b_emb + b_head);
+  unsigned char* d_mod = d_mod_in + b_mod;
+  char* dout = dp + in_bytes;
+  float* d_sim = (float*)(dout + o_sim);
+  float* d_disc = (float*)(dout + o_disc);
+  float* d_vs = (float*)(dout + o_vs);
+  int64_t* d_vr = (int64_t*)(dout + o_vr);
+  float* d_x = (float*)(dout + o_x);
+  float* d_probs = (float*)(dout + o_probs);
+  int32_t* d_verdict = (int32_t*)(dout + o_verdict);
+  float* d_conf = (float*)(dout + o_conf);
+
+  // straight from the caller's buffers: asynchronous DMA when they are pinned, staged by the driver otherwise
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_text, text_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, st));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_img, image_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, st));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_head, head_host, (size_t)n * 3 * 4, cudaMemcpyHostToDevice, st));
+  if (modality_host) MMF_CUDA_OK(h, cudaMemcpyAsync(d_mod_in, modality_host, (size_t)n, cudaMemcpyHostToDevice, st));
+
+  rc = mmf_cosine_pairs(h, d_text, d_img, n, MMF_DIM, 0.0, d_sim, nullptr, st);
+  if (rc != MMF_OK) return rc;
+  if (h->vault_loaded) {
+    rc = search_dispatch(h, d_img, n, top_k, threshold, algo, d_vs, d_vr, nullptr, d_disc, st, "score_batch_host");
+  } else {      // reference: vault_loaded == False -> zero discrepancy, no matches (misinfo_forensics.py:422-428)
+    rc = mmf_fill_empty(h, n, top_k, d_vs, d_vr, nullptr, d_disc, st);
+  }
+  if (rc != MMF_OK) return rc;
+  mmf::assemble_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_head, modality_host ? d_mod_in : nullptr, n, d_sim,
+                                                                          d_disc, d_x, d_mod);
+  MMF_LAUNCH_OK(h);
+  rc = mmf_verdict_batch(h, d_x, d_mod, n, d_probs, d_verdict, d_conf, st);
+  if (rc != MMF_OK) return rc;
+  char* hp = (char*)h->pinned;
+  MMF_CUDA_OK(h, cudaMemcpyAsync(hp, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+  MMF_CUDA_OK(h, cudaStreamSynchronize(st));
+  if (out_clip_similarity) memcpy(out_clip_similarity, hp + o_sim, (size_t)n * 4);
+  if (out_vault_discrepancy) memcpy(out_vault_discrepancy, hp + o_disc, (size_t)n * 4);
+  if (out_vault_scores) memcpy(out_vault_scores, hp + o_vs, (size_t)n * top_k * 4);
+  if (out_vault_rows) memcpy(out_vault_rows, hp + o_vr, (size_t)n * top_k * 8);
+  if (out_scores5) memcpy(out_scores5, hp + o_x, (size_t)n * 5 * 4);
+  memcpy(out_probs, hp + o_probs, (size_t)n * 2 * 4);
+  if (out_verdict) memcpy(out_verdict, hp + o_verdict, (size_t)n * 4);
+  if (out_confidence) memcpy(out_confidence, hp + o_conf, (size_t)n * 4);
+  return MMF_OK;
+}

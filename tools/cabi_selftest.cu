@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 
 #include "../include/mmf_b200.h"
@@ -278,6 +279,91 @@ int main(int argc, char** argv) {
     unsetenv("MMF_MMA_SCREEN");
     unsetenv("MMF_MMA_BOUND");
     unsetenv("MMF_MERGE_FAST");
+  }
+  // ---------------- mmf_score_batch_host (one call, host buffers) vs the device entry points
+  {
+    printf("[score_batch_host] vs cosine + search + fusion through the device entry points\n");
+    const int nq = 256, k = 10;
+    const long long n = 300000;
+    std::vector<float> w(MMF_FUSION_PARAMS);
+    for (int i = 0; i < MMF_FUSION_PARAMS; ++i) w[i] = 0.3f * sinf(0.37f * i + 1.0f);
+    MM(mmf_fusion_load(H, w.data()));
+    fill_rows<<<(unsigned)((n * 512 + 255) / 256), 256>>>(d_vault, n, 41);
+    fill_rows<<<(nq * 512 + 255) / 256, 256>>>(d_q, nq, 42);
+    plant_queries<<<(40 * 512 + 255) / 256, 256>>>(d_q, d_vault, 40, n / 40, 0.6f);
+    float* d_text = nullptr;
+    CK(cudaMalloc(&d_text, (size_t)nq * 512 * 4));
+    fill_rows<<<(nq * 512 + 255) / 256, 256>>>(d_text, nq, 43);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, n, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    std::vector<float> text((size_t)nq * 512), img((size_t)nq * 512), head((size_t)nq * 3);
+    std::vector<uint8_t> mod(nq);
+    CK(cudaMemcpy(text.data(), d_text, text.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(img.data(), d_q, img.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nq * 3; ++i) head[i] = 0.5f + 0.5f * sinf(1.3f * i);
+    for (int i = 0; i < nq; ++i) mod[i] = (uint8_t)(i % 4);
+    std::vector<float> sim(nq), disc(nq), vs((size_t)nq * k), x5((size_t)nq * 5), probs((size_t)nq * 2), conf(nq);
+    std::vector<int64_t> vr((size_t)nq * k);
+    std::vector<int32_t> verdict(nq);
+    // (a) no modality mask: every piece must equal the device entry point it is made of
+    MM(mmf_score_batch_host(H, text.data(), img.data(), head.data(), nullptr, nq, k, 0.85, MMF_ALGO_AUTO, sim.data(), disc.data(),
+                            vs.data(), vr.data(), x5.data(), probs.data(), verdict.data(), conf.data()));
+    Result ref = search(nq, k, MMF_ALGO_AUTO);
+    Result got;
+    got.scores = vs; got.rows = vr; got.disc = disc;
+    fails += !same(got, ref, nq, k, "vault part");
+    float* d_sim = nullptr; float* d_x = nullptr; float* d_p = nullptr;
+    CK(cudaMalloc(&d_sim, nq * 4)); CK(cudaMalloc(&d_x, nq * 5 * 4)); CK(cudaMalloc(&d_p, nq * 2 * 4));
+    MM(mmf_cosine_pairs(H, d_text, d_q, nq, 512, 0.0, d_sim, nullptr, nullptr));
+    std::vector<float> sim_ref(nq), probs_ref((size_t)nq * 2);
+    CK(cudaMemcpy(sim_ref.data(), d_sim, nq * 4, cudaMemcpyDeviceToHost));
+    long long bad = 0;
+    for (int i = 0; i < nq; ++i) {
+      bad += memcmp(&sim[i], &sim_ref[i], 4) != 0;
+      const float want[5] = {head[i * 3], head[i * 3 + 1], head[i * 3 + 2], sim_ref[i], ref.disc[i]};
+      bad += memcmp(&x5[(size_t)i * 5], want, 20) != 0;
+    }
+    CK(cudaMemcpy(d_x, x5.data(), x5.size() * 4, cudaMemcpyHostToDevice));
+    MM(mmf_fusion_forward(H, d_x, nq, d_p, nullptr, nullptr, nullptr));
+    CK(cudaMemcpy(probs_ref.data(), d_p, probs_ref.size() * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nq * 2; ++i) bad += memcmp(&probs[i], &probs_ref[i], 4) != 0;
+    for (int i = 0; i < nq; ++i) bad += verdict[i] != (probs[i * 2 + 1] > 0.5f) || conf[i] != (verdict[i] ? probs[i * 2 + 1] : probs[i * 2]);
+    printf("  cosine / assembled scores / fusion probabilities / verdicts: %lld differences -> %s\n", bad, bad ? "MISMATCH" : "identical");
+    fails += bad != 0;
+    // (b) modality mask: skipped modalities are zeroed, fallback verdict rule (misinfo_forensics.py:884-899)
+    MM(mmf_score_batch_host(H, text.data(), img.data(), head.data(), mod.data(), nq, k, 0.85, MMF_ALGO_AUTO, sim.data(), disc.data(),
+                            vs.data(), vr.data(), x5.data(), probs.data(), verdict.data(), conf.data()));
+    bad = 0;
+    for (int i = 0; i < nq; ++i) {
+      const bool t = mod[i] & 1, v = mod[i] & 2;
+      bad += sim[i] != ((t && v) ? sim_ref[i] : 0.f);
+      bad += disc[i] != (v ? ref.disc[i] : 0.f);
+      float fake;
+      if (mod[i] == 3) fake = probs_ref[i * 2 + 1];
+      else fake = fminf(1.f, fmaxf(0.f, mod[i] == 1 ? head[i * 3 + 1] : mod[i] == 2 ? fmaxf(head[i * 3 + 2], disc[i]) : 0.5f));
+      bad += probs[i * 2 + 1] != fake;
+    }
+    printf("  with a modality mask (text only / visual only / neither / both): %lld differences -> %s\n", bad, bad ? "MISMATCH" : "identical");
+    fails += bad != 0;
+    // time it: pageable host buffers here, so this is an upper bound for pinned ones
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float* pin = nullptr;
+    CK(cudaMallocHost(&pin, ((size_t)nq * 512 * 2 + nq * 3) * 4));
+    memcpy(pin, text.data(), text.size() * 4); memcpy(pin + (size_t)nq * 512, img.data(), img.size() * 4);
+    memcpy(pin + (size_t)nq * 1024, head.data(), head.size() * 4);
+    for (int rep = 0; rep < 3; ++rep)
+      MM(mmf_score_batch_host(H, pin, pin + (size_t)nq * 512, pin + (size_t)nq * 1024, nullptr, nq, k, 0.85, MMF_ALGO_AUTO, sim.data(),
+                              disc.data(), vs.data(), vr.data(), x5.data(), probs.data(), verdict.data(), conf.data()));
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int rep = 0; rep < 20; ++rep)
+      MM(mmf_score_batch_host(H, pin, pin + (size_t)nq * 512, pin + (size_t)nq * 1024, nullptr, nq, k, 0.85, MMF_ALGO_AUTO, sim.data(),
+                              disc.data(), vs.data(), vr.data(), x5.data(), probs.data(), verdict.data(), conf.data()));
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / 20;
+    printf("  end to end, pinned host buffers, %d queries x %lld rows: %.3f ms per call (%.0f queries/s)\n", nq, n, ms, nq / ms * 1e3);
+    cudaFreeHost(pin); cudaFree(d_text); cudaFree(d_sim); cudaFree(d_x); cudaFree(d_p);
   }
   // ---------------- peer-memory candidate exchange (csrc/exchange.cu): 2 ranks emulated on ONE device
   // (two handles, two streams, two buffers of this device).  Small query counts only: on one GPU the spinning
