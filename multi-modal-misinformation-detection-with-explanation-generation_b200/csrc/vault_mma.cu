@@ -66,9 +66,13 @@ constexpr int Q_RESIDENT_BYTES = (MMF_DIM / KBLK) * TILE_BYTES;   // 128 KB
 // even when the data is there, against 256 clk of MMA work per k-block)
 __host__ __device__ constexpr int kblk_per_stage(bool split) { return split ? 1 : 2; }
 __host__ __device__ constexpr int stage_bytes(bool split, int cg) { return (split ? 2 : 1) * TILE_BYTES / cg * kblk_per_stage(split); }
-__host__ __device__ constexpr int mma_stages(bool split, int cg) { return split ? 3 * cg : (cg == 1 ? 6 : 8); }
-__host__ __device__ constexpr int mma_smem_bytes(bool split, int cg) {
-  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg) * stage_bytes(split, cg);
+// deep (experimental, VAR_DEEP, pairs of the 1-plane pipeline only): 12 x 16 KB = 3 vault tiles in flight per CTA
+// instead of 2 -- the screening pass is HBM-latency-bound (ncu: DRAM 50 %, tensor pipe 58 %)
+__host__ __device__ constexpr int mma_stages(bool split, int cg, bool deep = false) {
+  return split ? 3 * cg : (cg == 1 ? 6 : (deep ? 12 : 8));
+}
+__host__ __device__ constexpr int mma_smem_bytes(bool split, int cg, bool deep = false) {
+  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg, deep) * stage_bytes(split, cg);
 }
 constexpr int NUM_KBLK = MMF_DIM / KBLK;     // 8
 constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter: a lone warp per scheduler cannot hide its own latency
@@ -378,12 +382,12 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 // and selects the top-k among them -- the result is the exact top-k, not an approximation.
 // If a band does not fit a candidate list, *p.ovf is set and the guarded (VAR_GUARD) 3-pass kernel redoes
 // the batch.
-constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4;
+constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4, VAR_DEEP = 8;
 template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
-  constexpr int STAGES = mma_stages(SPLIT, CG);
+  constexpr int STAGES = mma_stages(SPLIT, CG, (VAR & VAR_DEEP) != 0);
   constexpr int STAGE_BYTES = stage_bytes(SPLIT, CG);
   constexpr int KBS = kblk_per_stage(SPLIT);         // k-blocks per stage
   constexpr int PLANE_BYTES = TILE_BYTES / CG;       // one plane of this CTA's share of a B k-block
@@ -1227,7 +1231,7 @@ template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
                       cudaStream_t st) {
-  const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
+  const int smem = mma_smem_bytes(SPLIT, CG, (VAR & VAR_DEEP) != 0) + 256 + 1024;
   auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR, VAR>;
   MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg = {};
@@ -1351,7 +1355,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
     // 1 pass over the hi planes + exact re-scoring of the survivors; then the guarded 3-pass search, which
     // returns at once unless a candidate band overflowed (its bounds must restart from scratch: the
     // screening pass published bounds on APPROXIMATE scores)
-    rc = cg == 2 ? launch_mma<false, 8, 2, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+    bool deep = false;                // experimental (round 2 A/B): MMF_MMA_STAGES=12 -> deeper shared-memory ring
+    { const char* e = getenv("MMF_MMA_STAGES"); deep = e && atoi(e) == 12 && cg == 2; }
+    rc = deep    ? launch_mma<false, 8, 2, 16, VAR_SCREEN | VAR_DEEP>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
+                                                                      out_packed, out_disc, st)
+         : cg == 2 ? launch_mma<false, 8, 2, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
                                                            out_packed, out_disc, st)
                  : launch_mma<false, 8, 1, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
                                                            out_packed, out_disc, st);

@@ -189,6 +189,17 @@ int main(int argc, char** argv) {
     setenv("MMF_MMA_SCREEN", "0", 1);
     fails += !same(fast, stream, nq, k, "screened search + fast tail vs streaming kernel");
     printf("  search time with MMF_MERGE_FAST=1: %.3f ms (%.0f GB/s algorithmic)\n", ms_fast, rows_fp32 * 2048.0 / ms_fast * 1e-6);
+    float ms_deep = 0;
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    setenv("MMF_MERGE_FAST", "1", 1);
+    setenv("MMF_MMA_STAGES", "12", 1);
+    Result deep = search(nq, k, MMF_ALGO_MMA, &ms_deep, 20);
+    unsetenv("MMF_MMA_STAGES");
+    setenv("MMF_MERGE_FAST", "0", 1);
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    fails += !same(deep, stream, nq, k, "screened search, 12-stage ring vs streaming kernel");
+    printf("  search time with MMF_MMA_STAGES=12 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_deep,
+           rows_fp32 * 2048.0 / ms_deep * 1e-6);
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
     // band overflow: 3000 identical rows -> guarded 3-pass redo, ties by row id
