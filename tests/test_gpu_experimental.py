@@ -152,3 +152,47 @@ def test_screened_search_band_overflow_falls_back(eng):
     ri, rs, _ = oracle.vault_search_batched(vault, q, 10)
     assert_topk(got[1], got[0], ri, rs, FP32_TOL, "clustered vault")
     assert_close(got[0], exact[0], 5e-6, "clustered vault vs streaming kernel")
+
+
+# ------------------------------------------------------------------------------ one-call host entry, peer exchange (world 1)
+def test_score_batch_host_equals_score_batch(eng):
+    """Engine.score_batch_host (mmf_score_batch_host: one library call, host buffers) == mmf_b200.score_batch"""
+    n_rows, b, k = 50000, 200, 5
+    vault_rows = synth.vault_rows(n_rows, seed=41)
+    vault = mmf_b200.TruthVault(eng, vault_rows, None, mode="fp32")
+    eng.fusion_load(synth.fusion_state_dict(1))
+    q, _, _ = synth.queries(b, n_rows, seed=42, plant_frac=0.3, vault_seed=41)
+    text, _ = synth.caption_image_pairs(b, seed=43)
+    head = synth.head_scores(b, seed=44)
+    for modality in (None, (np.arange(b) % 4).astype(np.uint8)):
+        want = mmf_b200.score_batch(eng, vault, text, q, head, modality, k)
+        got = eng.score_batch_host(text, q, head, modality, k)
+        for key in ("clip_similarity", "vault_discrepancy", "vault_scores", "vault_rows", "scores", "probs", "verdict", "confidence"):
+            assert np.array_equal(got[key], npy(want[key]), equal_nan=True), key
+    # pinned torch tensors in, and no vault loaded -> zero discrepancy / no rows
+    eng.vault_unload()
+    got = eng.score_batch_host(torch.from_numpy(text).pin_memory(), torch.from_numpy(q).pin_memory(),
+                               torch.from_numpy(head).pin_memory(), None, k)
+    assert np.all(got["vault_rows"] == -1) and np.all(got["vault_discrepancy"] == 0) and np.all(np.isnan(got["vault_scores"]))
+
+
+def test_peer_exchange_single_rank_loopback(eng):
+    """csrc/exchange.cu with world = 1 (the only rank pushes into its own buffer): push, flag, wait-merge must give
+    the plain search result; three calls in a row cover both buffer parities"""
+    n_rows, nq = 30000, 40
+    vault = synth.vault_rows(n_rows, seed=51)
+    q, _, _ = synth.queries(nq, n_rows, seed=52, plant_frac=0.5, vault_seed=51)
+    eng.vault_load(vault, mode="fp32")
+    need = eng.exchange_layout(1, nq, 100)
+    buf = torch.zeros(need // 8 + 16, dtype=torch.int64, device="cuda")
+    eng.exchange_attach(0, 1, [buf.data_ptr()], buf.numel() * 8)
+    try:
+        for k in (10, 100, 5):
+            want = [npy(t) for t in eng.vault_search(q, k)]
+            for _ in range(3):
+                got = [npy(t) for t in eng.vault_search_exchange(q, k, k)]
+                assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want)), k
+        with pytest.raises(mmf_b200.MMFError):
+            eng.vault_search_exchange(np.zeros((100000, 512), np.float32), 100, 100)     # does not fit the attached buffer
+    finally:
+        eng.exchange_detach()
