@@ -322,10 +322,9 @@ __host__ __device__ __forceinline__ float hist_edge(int bin) {   // lower edge o
 // ---- query operand prep --------------------------------------------------------------------
 // One warp per padded query row: q / ||q|| (misinfo_forensics.py:439), then the MMA operand
 // planes: bf16 (1 plane) or fp16 hi/lo of q*2^8 (2 planes, plane p at row p*q_pad + i).
-__global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
-                                                             int split, void* __restrict__ planes,
-                                                             u32* __restrict__ g_tau, u32* __restrict__ pool,
-                                                             int top_k, int hist, float* __restrict__ qn) {
+__device__ __forceinline__ void prep_query_row(const float* __restrict__ q, int n_queries, int q_pad, int split,
+                                               void* __restrict__ planes, u32* __restrict__ g_tau, u32* __restrict__ pool,
+                                               int top_k, int hist, float* __restrict__ qn) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
@@ -358,6 +357,37 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
       reinterpret_cast<__nv_bfloat16*>(planes)[o] = __float2bfloat16_rn(x);
     }
   }
+}
+__global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
+                                                             int split, void* __restrict__ planes,
+                                                             u32* __restrict__ g_tau, u32* __restrict__ pool,
+                                                             int top_k, int hist, float* __restrict__ qn) {
+  prep_query_row(q, n_queries, q_pad, split, planes, g_tau, pool, top_k, hist, qn);
+}
+// LEAN launch sequence of the screened search (experimental, env MMF_MMA_LEAN=1): the prep kernel also clears the
+// candidate counters of both passes and the overflow flag (instead of three memsets) and initialises a SECOND set
+// of bounds for the guarded exact pass (instead of a second prep launch), so a search is 5 launches, not 9 stream
+// operations.
+__global__ void __launch_bounds__(256) mma_query_prep_lean_kernel(const float* __restrict__ q, int n_queries, int q_pad,
+                                                                  void* __restrict__ planes, u32* __restrict__ g_tau,
+                                                                  u32* __restrict__ pool, int top_k, float* __restrict__ qn,
+                                                                  int* __restrict__ zero_a, long long zero_a_n,
+                                                                  int* __restrict__ zero_b, long long zero_b_n,
+                                                                  u32* __restrict__ g_tau2, u32* __restrict__ pool2) {
+  const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+  for (long long i = gtid; i < zero_a_n; i += nthr) zero_a[i] = 0;
+  for (long long i = gtid; i < zero_b_n; i += nthr) zero_b[i] = 0;
+  const int lane = threadIdx.x & 31;
+  const int w = (int)(gtid >> 5);
+  if (w < q_pad) {                                  // bounds of the guarded pass: bucket pool (top_k <= 16)
+    if (lane == 0) g_tau2[w] = 0;
+    int pool_n = 16;
+    while (pool_n < top_k) pool_n <<= 1;
+#pragma unroll
+    for (int j = 0; j < MMF_MAX_TOP_K / 32; ++j)
+      pool2[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
+  }
+  prep_query_row(q, n_queries, q_pad, 1, planes, g_tau, pool, top_k, 0, qn);
 }
 
 // ---- the search kernel ---------------------------------------------------------------------
@@ -1314,7 +1344,14 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   { const char* e = getenv("MMF_MMA_SCREEN"); if (e && atoi(e) == 0) screen = false; }
   const size_t off_qn = off_cand + al((size_t)lists * C * 8);
   const size_t off_flag = off_qn + (screen ? al((size_t)p.q_pad * MMF_DIM * 4) : 0);
-  const size_t total = screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
+  bool lean = false;                  // experimental (round 2 A/B): 5-launch sequence, see mma_query_prep_lean_kernel
+  { const char* e = getenv("MMF_MMA_LEAN"); lean = screen && e && atoi(e) != 0; }
+  // lean: [flag 1 KB | cand_cnt of the guarded pass] (one contiguous region to clear) | g_tau2 | pool2
+  const size_t off_cnt2 = off_flag + 1024;
+  const size_t off_tau2 = off_cnt2 + al((size_t)lists * 4);
+  const size_t off_pool2 = off_tau2 + al((size_t)p.q_pad * 4);
+  const size_t total = lean ? off_pool2 + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4)
+                            : screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* sc = (char*)h->scratch;
@@ -1328,14 +1365,20 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.margin = screen ? 2.0f * SCREEN_EPS : 0.f;
   p.qn = screen ? (const float*)(sc + off_qn) : nullptr;
 
-  MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
+  if (!lean) MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
   // top_k > 16 (lazy thresholds): grid-wide bound from the score histogram (VAR_HIST); MMF_MMA_BOUND=pool selects the
   // bucket maxima of round 1 (A/B, triage)
   bool hist = top_k > 16;
   { const char* e = getenv("MMF_MMA_BOUND"); if (e && (e[0] == 'p' || e[0] == '0')) hist = false; }
-  if (screen) MMF_CUDA_OK(h, cudaMemsetAsync(p.ovf, 0, 4, st));
-  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
-                                                           p.pool, top_k, hist ? 1 : 0, screen ? (float*)(sc + off_qn) : nullptr);
+  if (lean) {
+    mma_query_prep_lean_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(
+        queries, p.n_queries, p.q_pad, planes, p.g_tau, p.pool, top_k, (float*)(sc + off_qn), p.cand_cnt, (long long)lists,
+        (int*)(sc + off_flag), (long long)(256 + lists), (u32*)(sc + off_tau2), (u32*)(sc + off_pool2));
+  } else {
+    if (screen) MMF_CUDA_OK(h, cudaMemsetAsync(p.ovf, 0, 4, st));
+    mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
+                                                             p.pool, top_k, hist ? 1 : 0, screen ? (float*)(sc + off_qn) : nullptr);
+  }
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;
@@ -1364,10 +1407,16 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                  : launch_mma<false, 8, 1, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
                                                            out_packed, out_disc, st);
     if (rc != MMF_OK) return rc;
-    MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));
-    mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, 1, planes, p.g_tau, p.pool,
-                                                             top_k, 0, nullptr);
-    MMF_LAUNCH_OK(h);
+    if (lean) {                       // the guarded pass has its own counters and bounds, prepared by the first kernel
+      p.cand_cnt = (int*)(sc + off_cnt2);
+      p.g_tau = (u32*)(sc + off_tau2);
+      p.pool = (u32*)(sc + off_pool2);
+    } else {
+      MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));
+      mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, 1, planes, p.g_tau, p.pool,
+                                                               top_k, 0, nullptr);
+      MMF_LAUNCH_OK(h);
+    }
     return cg == 2 ? launch_mma<true, 8, 2, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
                                                            out_packed, out_disc, st)
                    : launch_mma<true, 8, 1, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,

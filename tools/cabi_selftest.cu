@@ -200,6 +200,17 @@ int main(int argc, char** argv) {
     fails += !same(deep, stream, nq, k, "screened search, 12-stage ring vs streaming kernel");
     printf("  search time with MMF_MMA_STAGES=12 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_deep,
            rows_fp32 * 2048.0 / ms_deep * 1e-6);
+    float ms_lean = 0;
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    setenv("MMF_MERGE_FAST", "1", 1);
+    setenv("MMF_MMA_LEAN", "1", 1);
+    Result lean = search(nq, k, MMF_ALGO_MMA, &ms_lean, 20);
+    unsetenv("MMF_MMA_LEAN");
+    setenv("MMF_MERGE_FAST", "0", 1);
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    fails += !same(lean, stream, nq, k, "screened search, lean launch sequence vs streaming kernel");
+    printf("  search time with MMF_MMA_LEAN=1 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_lean,
+           rows_fp32 * 2048.0 / ms_lean * 1e-6);
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
     // band overflow: 3000 identical rows -> guarded 3-pass redo, ties by row id
@@ -212,6 +223,14 @@ int main(int argc, char** argv) {
     Result screen2 = search(nq, k, MMF_ALGO_MMA);
     unsetenv("MMF_MMA_SCREEN");
     fails += !same(screen2, mma2, nq, k, "screened search, overflowing band vs 3-pass");
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    setenv("MMF_MMA_LEAN", "1", 1);
+    Result lean2 = search(nq, k, MMF_ALGO_MMA);
+    Result lean3 = search(nq, k, MMF_ALGO_MMA);       // twice: the flag and both counter sets must reset
+    unsetenv("MMF_MMA_LEAN");
+    unsetenv("MMF_MMA_SCREEN");
+    fails += !same(lean2, mma2, nq, k, "lean sequence, overflowing band vs 3-pass");
+    fails += !same(lean3, mma2, nq, k, "lean sequence, overflowing band, second call");
     printf("  query 0 top rows: %lld %lld %lld (expect 72999 72998 72997)\n", (long long)screen2.rows[0],
            (long long)screen2.rows[1], (long long)screen2.rows[2]);
     fails += screen2.rows[0] != 72999;
@@ -275,6 +294,12 @@ int main(int argc, char** argv) {
         setenv("MMF_MERGE_FAST", "1", 1);
         Result fast = search(sh.nq, sh.k, MMF_ALGO_MMA);
         setenv("MMF_MERGE_FAST", "0", 1);
+        if (mode == 0 && sh.k <= 16) {
+          setenv("MMF_MMA_LEAN", "1", 1);
+          Result lean = search(sh.nq, sh.k, MMF_ALGO_MMA);
+          unsetenv("MMF_MMA_LEAN");
+          fails += !same(lean, var, sh.nq, sh.k, "   + MMF_MMA_LEAN=1");
+        }
         char what_fast[112];
         snprintf(what_fast, sizeof what_fast, "   + MMF_MERGE_FAST=1");
         fails += !same(fast, var, sh.nq, sh.k, what_fast);
