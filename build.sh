@@ -22,3 +22,5 @@ echo "built $OUT"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/cabi_selftest tools/cabi_selftest.cu \
   -L"$PKG" -lmmf_b200 -Xlinker -rpath -Xlinker "\$ORIGIN/../$PKG"
 echo "built tools/cabi_selftest"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -o tools/hbm_stride_micro tools/hbm_stride_micro.cu
+echo "built tools/hbm_stride_micro"
