@@ -161,6 +161,17 @@ extern "C" int mmf_exchange_attach(mmf_handle* h, int rank, int world, const uin
   x->world = world;
   x->bytes_per_rank = (size_t)bytes_per_rank;
   x->epoch = 0;
+  // this rank's candidates of one exchange can never exceed one slot of the attached buffer: size the local
+  // buffer for that now, so that the (asynchronous) search path never allocates or synchronises
+  const size_t local_cap = ((size_t)bytes_per_rank - MMF_XCHG_HEADER) / 2 / (size_t)world + 1024;
+  if (local_cap > x->local_bytes) {
+    MMF_CUDA_OK(h, cudaDeviceSynchronize());
+    if (x->local) MMF_CUDA_OK(h, cudaFree(x->local));
+    x->local = nullptr;
+    x->local_bytes = 0;
+    MMF_CUDA_OK(h, cudaMalloc(&x->local, local_cap));
+    x->local_bytes = local_cap;
+  }
   memset(&x->peers, 0, sizeof x->peers);
   for (int r = 0; r < world; ++r) x->peers.base[r] = reinterpret_cast<unsigned char*>((uintptr_t)peer_ptrs[r]);
   // the flags of THIS rank start at 0 (= no exchange seen); the caller barriers after attaching
@@ -199,14 +210,8 @@ extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, in
     return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: %lld bytes of peer buffer needed, %zu attached",
                          (long long)need, x->bytes_per_rank);
   const size_t local_bytes = (size_t)n_queries * k_local * 8;
-  if (local_bytes > x->local_bytes) {
-    MMF_CUDA_OK(h, cudaDeviceSynchronize());
-    if (x->local) MMF_CUDA_OK(h, cudaFree(x->local));
-    x->local = nullptr;
-    x->local_bytes = 0;
-    MMF_CUDA_OK(h, cudaMalloc(&x->local, local_bytes));
-    x->local_bytes = local_bytes;
-  }
+  if (local_bytes > x->local_bytes)      // cannot happen after the size check above (attach sized it for one slot)
+    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: local candidate buffer too small");
   // 1. local search of this rank's shard -> packed candidates with GLOBAL row ids
   int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)x->local, st, "vault_search_exchange");
   if (rc != MMF_OK) return rc;

@@ -135,6 +135,7 @@ int main(int argc, char** argv) {
   const long long rows_bf16_a = argc > 2 ? atoll(argv[2]) : 1250000;
   const long long rows_bf16_b = argc > 3 ? atoll(argv[3]) : 0;      // optional second bf16 size (e.g. 10000000)
   int fails = 0;
+  setvbuf(stdout, nullptr, _IOLBF, 0);     // a timeout must not eat the lines already printed
   printf("%s\n", mmf_version());
   setenv("MMF_MERGE_FAST", "0", 1);        // every arm below names its switches explicitly
   { int rc = mmf_create(0, &H); if (rc != MMF_OK) { printf("mmf_create failed: %s\n", mmf_status_string(rc)); return 1; } }
@@ -441,6 +442,13 @@ int main(int argc, char** argv) {
         const int k = ks[t];
         for (int algo = MMF_ALGO_STREAM; algo <= MMF_ALGO_MMA; ++algo) {
           Result full = search(nq, k, algo);
+          // one process plays both ranks here: anything that synchronises the DEVICE between enqueueing rank 0 and
+          // rank 1 (scratch growth on a first call) would wait for rank 0's spinning merge forever -> warm up first
+          for (int r = 0; r < 2; ++r) {
+            int rc = mmf_vault_search(R[r], d_q, nq, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
+            if (rc != MMF_OK) { printf("warm-up search failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+          }
+          CK(cudaDeviceSynchronize());
           for (int rep = 0; rep < 3; ++rep) {       // 3 back-to-back exchanges: both parities + buffer reuse
             for (int r = 0; r < 2; ++r) {
               int rc = mmf_vault_search_exchange(R[r], d_q, nq, k, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
