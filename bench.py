@@ -159,7 +159,10 @@ def run_reference_arm(args, wl):
         "impl": "reference", "metric": "vault queries/s", "value": value, "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "vault_rows": rows, "dim": 512, "top_k": k},
+        "config": {"workload": wl["desc"], "queries_per_step": n_sample, "vault_rows_total": rows, "vault_rows_per_gpu": rows,
+                   "dim": 512, "top_k": k, "vault_mode": wl["mode"], "algo": "reference as shipped (NumPy, per-query renormalisation)",
+                   "parallelism": "host CPU, %d cores (BLAS threads)" % cores,
+                   "sample": "each step = %d query of the workload's %d-query batch against the full vault" % (n_sample, wl["q"])},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
