@@ -185,6 +185,11 @@ int mmf_mma_plan_check(int64_t n_queries, int64_t n_rows, int sm_count, int64_t*
  * histogram yields, -inf when it yields none.  Same binning code as the kernel; needs no GPU. */
 int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, float* out_bound);
 
+/* The error bound eps (score units) of the screened fp32-exact search: |one-pass fp16 hi-plane score - exact
+ * score| <= eps for unit-norm rows and queries; rows within 2*eps of the k-th best approximate score are
+ * re-scored exactly.  Host-only. */
+double mmf_mma_screen_eps(void);
+
 /* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
 int64_t mmf_launch_count(const mmf_handle* h);
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "mmf_score_batch_host": (_i, [_p, _p, _p, _p, _p, _l, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "mmf_mma_plan_check": (_i, [_l, _l, _i, C.POINTER(_l), C.POINTER(_i), C.POINTER(_i)]),
     "mmf_mma_hist_bound": (_i, [_p, _l, _i, C.POINTER(C.c_float)]),
+    "mmf_mma_screen_eps": (_d, []),
     "mmf_launch_count": (_l, [_p]),
 }
 

@@ -1257,6 +1257,10 @@ extern "C" int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, flo
   return MMF_OK;
 }
 
+// The error bound the screened search uses (score units), for the CPU test of the argument in DESIGN.md section 9.
+constexpr float SCREEN_EPS = 1.05e-3f;
+extern "C" double mmf_mma_screen_eps(void) { return (double)SCREEN_EPS; }
+
 template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
@@ -1308,7 +1312,7 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
 //                         <= 2 * 2^-11 * (1 + 2^-10) + 2^-22 < 9.78e-4,
 // plus the tensor core's fp32 accumulation error over 32 K-steps (measured 2.5e-6, budgeted 2e-5) and the fp32
 // rounding of the exact re-scoring (~2e-7).  Measured worst case on random and clustered vaults: 1.0e-4.
-constexpr float SCREEN_EPS = 1.05e-3f;
+// (SCREEN_EPS itself is defined above launch_mma.)
 
 int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
                    float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc, cudaStream_t st) {

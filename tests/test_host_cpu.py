@@ -211,3 +211,47 @@ def test_exchange_layout_and_argument_checks():
     assert lib.mmf_exchange_detach(None) == 0
     with pytest.raises(ValueError):
         mmf_b200.TruthVault(None, np.zeros((4, 512), np.float32), exchange="carrier-pigeon")
+
+
+def test_screened_search_argument_holds_on_emulated_operands():
+    """DESIGN.md section 9, checked on the CPU with the operands the kernels really use (fp16 hi/lo split of the
+    fp32-normalised rows x 2^8): the one-pass hi-plane score stays within the library's error bound of the exact
+    score, and 'keep everything within 2*eps of the k-th best approximate score, re-score exactly, take the top-k'
+    returns the exact top-k -- on random, tightly clustered and duplicate-heavy vaults"""
+    lib = _lib.load()
+    eps = lib.mmf_mma_screen_eps()
+    assert 9.78e-4 < eps < 2e-3                       # above the Cauchy-Schwarz bound 2*2^-11*(1+2^-10)+2^-22, not sloppy
+    r = np.random.default_rng(0)
+
+    def split(x):                                     # vault_build.cu / mma_query_prep_kernel
+        y = (x * np.float32(256.0)).astype(np.float32)
+        hi = y.astype(np.float16)
+        lo = (y - hi.astype(np.float32)).astype(np.float16)
+        return hi, lo
+
+    def unit(x):
+        x = x.astype(np.float32)
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    n, k = 60000, 10
+    base = r.standard_normal((n, 512)).astype(np.float32)
+    centres = r.standard_normal((20, 512)).astype(np.float32)
+    vaults = {"random": base,
+              "clustered": centres[r.integers(0, 20, n)] + 0.05 * base,
+              "duplicates": np.concatenate([base[:n - 3000], np.repeat(base[7:8], 3000, axis=0)])}
+    for name, v in vaults.items():
+        q = r.standard_normal((24, 512)).astype(np.float32)
+        q[:8] = v[r.integers(0, n, 8)] + 0.1 * q[:8]
+        q[8] = v[7]
+        vh, vl = split(unit(v))
+        qh, _ = split(unit(q))
+        exact = unit(q).astype(np.float64) @ ((vh.astype(np.float64) + vl.astype(np.float64)) / 256.0).T
+        approx = (qh.astype(np.float64) @ vh.astype(np.float64).T) / 65536.0
+        assert np.abs(approx - exact).max() < eps / 4, name          # measured ~1e-4: the bound has head-room
+        for i in range(q.shape[0]):
+            t = np.sort(approx[i])[-k]
+            band = np.nonzero(approx[i] >= t - 2 * eps)[0]
+            want = np.argsort(exact[i], kind="stable")[-k:]
+            assert set(want) <= set(band), (name, i)
+            got = band[np.argsort(exact[i][band], kind="stable")[-k:]]
+            assert np.array_equal(np.sort(exact[i][got]), np.sort(exact[i][want])), (name, i)
