@@ -179,6 +179,10 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// L2 prefetch of one box of a 3-D tensor map: no shared memory, no barrier -- the data only moves DRAM -> L2
+__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -412,7 +416,11 @@ __global__ void __launch_bounds__(256) mma_query_prep_lean_kernel(const float* _
 // and selects the top-k among them -- the result is the exact top-k, not an approximation.
 // If a band does not fit a candidate list, *p.ovf is set and the guarded (VAR_GUARD) 3-pass kernel redoes
 // the batch.
-constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4, VAR_DEEP = 8;
+// VAR_PREFETCH (experimental, screening pass, env MMF_MMA_PREFETCH=1): the producer asks for the vault tile it will
+// need PREFETCH_TILES tiles from now to be pulled into L2 (cp.async.bulk.prefetch.tensor), so that the DRAM latency
+// is hidden by L2 capacity (a few MB per SM-pair in flight) instead of by the 2-tile shared-memory ring.
+constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4, VAR_DEEP = 8, VAR_PREFETCH = 16;
+constexpr int PREFETCH_TILES = 4;
 template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -506,6 +514,14 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ++strip;
         }
         const int brow = vt * TILE_N + (int)rank * B_ROWS;
+        if constexpr ((VAR & VAR_PREFETCH) != 0 && (VAR & VAR_SCREEN) != 0) {
+          // same strip, PREFETCH_TILES ahead (the few tiles around a strip change simply go unprefetched)
+          if (u + PREFETCH_TILES < sch.n_tiles && vt + PREFETCH_TILES < sch.v_hi) {
+            const int prow = (vt + PREFETCH_TILES) * TILE_N + (int)rank * B_ROWS;
+#pragma unroll
+            for (int kb = 0; kb < NUM_KBLK; ++kb) tma_prefetch_l2_3d(&tm_b, kb * KBLK, 0, prow);
+          }
+        }
         for (int kb = 0; kb < NUM_KBLK; kb += KBS, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
@@ -1404,12 +1420,16 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
     // screening pass published bounds on APPROXIMATE scores)
     bool deep = false;                // experimental (round 2 A/B): MMF_MMA_STAGES=12 -> deeper shared-memory ring
     { const char* e = getenv("MMF_MMA_STAGES"); deep = e && atoi(e) == 12 && cg == 2; }
-    rc = deep    ? launch_mma<false, 8, 2, 16, VAR_SCREEN | VAR_DEEP>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
-                                                                      out_packed, out_disc, st)
-         : cg == 2 ? launch_mma<false, 8, 2, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
-                                                           out_packed, out_disc, st)
-                 : launch_mma<false, 8, 1, 16, VAR_SCREEN>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
-                                                           out_packed, out_disc, st);
+    bool pref = false;                // experimental (round 2 A/B): MMF_MMA_PREFETCH=1 -> L2 prefetch of the vault tiles
+    { const char* e = getenv("MMF_MMA_PREFETCH"); pref = e && atoi(e) != 0 && cg == 2; }
+#define MMF_SCREEN_LAUNCH(CG_, VAR_) \
+  launch_mma<false, 8, CG_, 16, VAR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, out_disc, st)
+    rc = (deep && pref) ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_DEEP | VAR_PREFETCH)
+         : deep         ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_DEEP)
+         : pref         ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_PREFETCH)
+         : cg == 2      ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN)
+                        : MMF_SCREEN_LAUNCH(1, VAR_SCREEN);
+#undef MMF_SCREEN_LAUNCH
     if (rc != MMF_OK) return rc;
     if (lean) {                       // the guarded pass has its own counters and bounds, prepared by the first kernel
       p.cand_cnt = (int*)(sc + off_cnt2);

@@ -201,6 +201,21 @@ int main(int argc, char** argv) {
     fails += !same(deep, stream, nq, k, "screened search, 12-stage ring vs streaming kernel");
     printf("  search time with MMF_MMA_STAGES=12 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_deep,
            rows_fp32 * 2048.0 / ms_deep * 1e-6);
+    float ms_pref = 0, ms_both = 0;
+    setenv("MMF_MMA_SCREEN", "1", 1);
+    setenv("MMF_MERGE_FAST", "1", 1);
+    setenv("MMF_MMA_PREFETCH", "1", 1);
+    Result pref = search(nq, k, MMF_ALGO_MMA, &ms_pref, 20);
+    setenv("MMF_MMA_STAGES", "12", 1);
+    Result both = search(nq, k, MMF_ALGO_MMA, &ms_both, 20);
+    unsetenv("MMF_MMA_STAGES");
+    unsetenv("MMF_MMA_PREFETCH");
+    setenv("MMF_MERGE_FAST", "0", 1);
+    setenv("MMF_MMA_SCREEN", "0", 1);
+    fails += !same(pref, stream, nq, k, "screened search, L2 prefetch vs streaming kernel");
+    fails += !same(both, stream, nq, k, "screened search, L2 prefetch + 12-stage ring");
+    printf("  search time with MMF_MMA_PREFETCH=1: %.3f ms (%.0f GB/s algorithmic); + MMF_MMA_STAGES=12: %.3f ms (%.0f GB/s)\n",
+           ms_pref, rows_fp32 * 2048.0 / ms_pref * 1e-6, ms_both, rows_fp32 * 2048.0 / ms_both * 1e-6);
     float ms_lean = 0;
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
