@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""A/B timing of the experimental kernel variants against the defaults (one GPU).
+"""A/B timing of the kernel variants behind environment switches (one GPU), through the Python API.
+(tools/cabi_selftest does the same comparisons without torch, in seconds.)
 
     python tools/ab_experimental.py            # both experiments, prints one JSON line each
     python tools/ab_experimental.py hist       # C4 shard shapes: bucket pool vs histogram bound (top-100, bf16)
@@ -62,7 +63,8 @@ def run_hist(eng):
         eng.vault_load(vault, mode="bf16")
         del vault
         q = torch.randn(4096, 512, device="cuda", generator=g)
-        base = eng.vault_search(q, 100, algo="mma")
+        with env(MMF_MMA_BOUND="pool"):
+            base = eng.vault_search(q, 100, algo="mma")
         with env(MMF_MMA_BOUND="hist"):
             got = eng.vault_search(q, 100, algo="mma")
         same = all(torch.equal(a, b) for a, b in zip(base, got))
@@ -83,7 +85,13 @@ def run_screen(eng):
     with env(MMF_MMA_SCREEN="1"):
         got = eng.vault_search(q, 10, algo="mma")
     same = all(torch.equal(a, b) for a, b in zip(exact, got))
-    ms = ab(eng, q, 10, [("3pass", {"MMF_MMA_SCREEN": "0"}), ("screen", {"MMF_MMA_SCREEN": "1"})])
+    ms = ab(eng, q, 10, [("3pass", {"MMF_MMA_SCREEN": "0"}), ("screen", {"MMF_MMA_SCREEN": "1"}),
+                         ("screen+12stages", {"MMF_MMA_SCREEN": "1", "MMF_MMA_STAGES": "12"}),
+                         ("screen+prefetch", {"MMF_MMA_SCREEN": "1", "MMF_MMA_PREFETCH": "1"}),
+                         ("screen+prefetch+12stages", {"MMF_MMA_SCREEN": "1", "MMF_MMA_PREFETCH": "1", "MMF_MMA_STAGES": "12"}),
+                         ("screen+lean", {"MMF_MMA_SCREEN": "1", "MMF_MMA_LEAN": "1"}),
+                         ("screen+prefetch+12stages+lean", {"MMF_MMA_SCREEN": "1", "MMF_MMA_PREFETCH": "1",
+                                                            "MMF_MMA_STAGES": "12", "MMF_MMA_LEAN": "1"})])
     print(json.dumps({"experiment": "screened fp32-exact search, 256 queries x 1M rows, top-10",
                       "identical_to_stream_kernel": same, "ms": ms,
                       "queries_per_s": {n: 256 / (t * 1e-3) for n, t in ms.items()},
