@@ -1,0 +1,38 @@
+#!/usr/bin/env bash
+# One-GPU validation + measurement battery (run from the repo root on a B200 box, e.g.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_battery.sh' ).  Every step has its own timeout and log under
+# gpurun_out/; a failing step does not stop the later ones.  Order = cheapest and most informative first.
+set -u
+mkdir -p gpurun_out
+run() {  # run <seconds> <log> <command...>
+  local t=$1 log=$2; shift 2
+  echo "=== $* (timeout ${t}s) -> gpurun_out/$log"
+  timeout "$t" "$@" > "gpurun_out/$log" 2>&1
+  echo "    rc=$?"
+}
+# 1. torch-free: every kernel variant against the others bit for bit, host entry, emulated 2-rank exchange, timings
+run 180 selftest.log tools/cabi_selftest 1000000 1250000 10000000
+grep -E "MISMATCH|selftest|search time|end to end" gpurun_out/selftest.log | tail -30
+# 2. does 1 KB of every 2 KB cost HBM efficiency?
+run 60 hbm_stride.log tools/hbm_stride_micro
+cat gpurun_out/hbm_stride.log
+# 3. the parity suites
+run 900 pytest_gpu.log python -m pytest tests -m gpu -x -q
+tail -3 gpurun_out/pytest_gpu.log
+MMF_EXPERIMENTAL=1 run 600 pytest_experimental.log python -m pytest tests/test_gpu_experimental.py -q
+tail -3 gpurun_out/pytest_experimental.log
+# 4. bench lines: default workload with both e2e paths, batch-1 latency mode, 10M-row bf16 on one GPU
+run 300 bench_c2.json python bench.py
+run 200 bench_c2_e2e_host.json python bench.py --e2e-api host --no-cpu-baseline
+run 200 bench_c3.json python bench.py --workload c3 --no-cpu-baseline
+run 400 bench_c4_n1.json python bench.py --workload c4 --no-cpu-baseline --steps 10
+run 120 bench_reference.json python bench.py --impl reference --steps 5 --warmup 1
+for f in bench_c2 bench_c2_e2e_host bench_c3 bench_c4_n1; do tail -c 1200 "gpurun_out/$f.json"; echo; done
+# 5. A/B of the experiments through the Python API
+run 300 ab_experimental.log python tools/ab_experimental.py
+cat gpurun_out/ab_experimental.log
+# 6. ncu: launch list of the default bench command, full capture of the dominant kernels (after everything passed)
+run 300 ncu_launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  --log-file gpurun_out/c2_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline
+run 200 ncu_full.log ncu --set full --clock-control none --import-source on -k regex:vault_mma_topk -c 3 -f \
+  -o gpurun_out/c2_c4shard_full tools/cabi_selftest profile
