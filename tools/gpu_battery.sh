@@ -27,7 +27,8 @@ run 200 bench_c2_e2e_host.json python bench.py --e2e-api host --no-cpu-baseline
 run 200 bench_c3.json python bench.py --workload c3 --no-cpu-baseline
 run 400 bench_c4_n1.json python bench.py --workload c4 --no-cpu-baseline --steps 10
 run 120 bench_reference.json python bench.py --impl reference --steps 5 --warmup 1
-for f in bench_c2 bench_c2_e2e_host bench_c3 bench_c4_n1; do tail -c 1200 "gpurun_out/$f.json"; echo; done
+run 400 bench_c5.json python tools/bench_c5.py --autocast
+for f in bench_c2 bench_c2_e2e_host bench_c3 bench_c4_n1 bench_c5; do tail -c 1200 "gpurun_out/$f.json"; echo; done
 # 5. A/B of the experiments through the Python API
 run 300 ab_experimental.log python tools/ab_experimental.py
 cat gpurun_out/ab_experimental.log
