@@ -65,6 +65,19 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {   // read-once dat
 
 }  // namespace mmf
 
+// ---- fused candidate push (exchange.cu <-> vault_mma.cu) ----------------------------------
+// When set on the handle during a search, the merge tail of the tcgen05 search writes its per-query winners
+// straight into slot [rank] of every rank's gather buffer and the last block publishes the epoch flags -- the
+// separate push kernel of exchange.cu is then not launched (push_fused reports that it happened).
+#define MMF_XCHG_MAX_WORLD 16
+struct mmf_push_ctx {
+  unsigned char* base[MMF_XCHG_MAX_WORLD];   // rank r's exchange buffer as mapped in this process
+  int rank, world, parity;
+  unsigned epoch;
+  size_t slot_off;                           // byte offset of slot [rank] of gather[parity] in every buffer
+  unsigned* done;                            // ticket counter (device, self-resetting)
+};
+
 // ---- handle ----------------------------------------------------------------------------
 struct mmf_handle {
   int device = -1;
@@ -95,6 +108,8 @@ struct mmf_handle {
   void* mma_state = nullptr;
   // peer-memory candidate exchange (exchange.cu), null until mmf_exchange_attach
   void* xchg_state = nullptr;
+  const mmf_push_ctx* push_ctx = nullptr;   // non-null only inside mmf_vault_search_exchange (fused push requested)
+  bool push_fused = false;
 };
 
 int mmf_set_error(mmf_handle* h, int status, const char* fmt, ...);

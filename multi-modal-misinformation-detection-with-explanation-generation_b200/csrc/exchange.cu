@@ -34,11 +34,11 @@
 #include "topk.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
-#define MMF_XCHG_MAX_WORLD 16
-#define MMF_XCHG_HEADER 1024
+#define MMF_XCHG_HEADER 1024      // MMF_XCHG_MAX_WORLD: common.cuh
 
 int mmf_search_dispatch_packed(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int algo,
                                uint64_t* out_packed, cudaStream_t st, const char* who);
@@ -70,7 +70,7 @@ __device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
 
 // n = n_queries * top_k keys of this rank -> slot [rank] of gather[parity] on every rank (own copy included,
 // so that the merge reads one layout).  Stores to one peer are contiguous: 8 B per thread, coalesced.
-__global__ void __launch_bounds__(256) exchange_push_kernel(const u64* __restrict__ local, long long n, ExchangePeers peers,
+__global__ void __launch_bounds__(256) exchange_push_kernel(const u64* local, long long n, ExchangePeers peers,
                                                             int rank, int world, size_t slot_off, int parity, u32 epoch,
                                                             u32* done) {
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256) exchange_push_kernel(const u64* __restric
 #pragma unroll 1
     for (int r = 0; r < world; ++r) {
       const int peer = (rank + r) % world;                     // start with the own copy, spread the links
-      reinterpret_cast<u64*>(peers.base[peer] + slot_off)[i] = key;
+      u64* dst = reinterpret_cast<u64*>(peers.base[peer] + slot_off) + i;
+      if (dst != local + i) *dst = key;                        // (the candidates may already sit in the own slot)
     }
   }
   __threadfence_system();                                      // this thread's peer stores, system scope
@@ -212,18 +213,32 @@ extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, in
   const size_t local_bytes = (size_t)n_queries * k_local * 8;
   if (local_bytes > x->local_bytes)      // cannot happen after the size check above (attach sized it for one slot)
     return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: local candidate buffer too small");
-  // 1. local search of this rank's shard -> packed candidates with GLOBAL row ids
-  int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)x->local, st, "vault_search_exchange");
-  if (rc != MMF_OK) return rc;
-  // 2. push into every rank's gather buffer + publish, 3. wait for everybody's + merge
   const u32 epoch = ++x->epoch;
   const int parity = (int)(epoch & 1u);
   const size_t gather_off = MMF_XCHG_HEADER + (size_t)parity * (size_t)per_parity;
   const size_t slot_off = gather_off + (size_t)x->rank * local_bytes;
-  const long long n = (long long)n_queries * k_local;
-  const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
-  exchange_push_kernel<<<blocks, 256, 0, st>>>(x->local, n, x->peers, x->rank, x->world, slot_off, parity, epoch, x->done);
-  MMF_LAUNCH_OK(h);
+  // 1. local search of this rank's shard -> packed candidates with GLOBAL row ids.
+  //    MMF_EXCHANGE_FUSED=1 (experimental): the search writes them into this rank's own slot and, where its merge
+  //    tail supports it (tcgen05 search, top_k > 16), pushes them to the peers and publishes the flags itself.
+  bool want_fused = false;
+  { const char* e = getenv("MMF_EXCHANGE_FUSED"); want_fused = e && atoi(e) != 0 && n_queries <= 65536; }
+  mmf_push_ctx ctx;
+  memset(&ctx, 0, sizeof ctx);
+  for (int r = 0; r < x->world; ++r) ctx.base[r] = x->peers.base[r];
+  ctx.rank = x->rank; ctx.world = x->world; ctx.parity = parity; ctx.epoch = epoch; ctx.slot_off = slot_off; ctx.done = x->done;
+  u64* packed = want_fused ? reinterpret_cast<u64*>(x->peers.base[x->rank] + slot_off) : x->local;
+  h->push_fused = false;
+  h->push_ctx = want_fused ? &ctx : nullptr;
+  int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)packed, st, "vault_search_exchange");
+  h->push_ctx = nullptr;
+  if (rc != MMF_OK) return rc;
+  // 2. push into every rank's gather buffer + publish (unless the search's tail already did), 3. wait + merge
+  if (!h->push_fused) {
+    const long long n = (long long)n_queries * k_local;
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
+    exchange_push_kernel<<<blocks, 256, 0, st>>>(packed, n, x->peers, x->rank, x->world, slot_off, parity, epoch, x->done);
+    MMF_LAUNCH_OK(h);
+  }
   exchange_wait_merge_kernel<<<(unsigned)n_queries, 256, 0, st>>>(x->peers.base[x->rank], x->world, gather_off, parity, epoch,
                                                                  (long long)n_queries, k_local, top_k, threshold, out_scores,
                                                                  (long long*)out_rows, out_discrepancy);

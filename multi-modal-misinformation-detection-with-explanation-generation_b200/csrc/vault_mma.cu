@@ -988,6 +988,65 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
                     threshold);
 }
 
+// Merge tail fused with the candidate push of the row-sharded search (experimental, MMF_EXCHANGE_FUSED=1; see
+// exchange.cu for the protocol): the FAST merge of one query, then its top_k winners go straight from shared
+// memory into slot [rank] of EVERY rank's gather buffer (the own one included) -- the transfer of query i overlaps
+// the selection of the other queries -- and the last block publishes this rank's epoch flag on every rank.
+template <int KPL, int CG>
+__global__ void __launch_bounds__(256) mma_merge_push_kernel(const MmaParams p, int n_pairs, const mmf_push_ctx px) {
+  constexpr int C = 32 * KPL;
+  __shared__ SelectSmem sel;
+  __shared__ u64 staging[4096];
+  __shared__ int slots[MERGE_MAX_SLOTS];
+  __shared__ int n_slots;
+  __shared__ bool last;
+  const int qg = blockIdx.x;
+  const int qt = qg / TILE_M, m = qg % TILE_M;
+  const int tp = qt / CG, r = qt % CG;
+  if (threadIdx.x == 0) n_slots = 0;
+  __syncthreads();
+  gather_slots_par(p, n_pairs, tp, slots, &n_slots);
+  __syncthreads();
+  CandidateLists src;
+  const long long base = (long long)r * TILE_M + m;
+  src.lists = p.cand + base * C;
+  src.counts = p.cand_cnt + base;
+  src.n_lists = min(n_slots, MERGE_MAX_SLOTS);
+  src.k_in = C;
+  src.list_stride = (long long)CG * TILE_M * C;
+  src.count_stride = CG * TILE_M;
+  src.slots = slots;
+  const u32 n = stage_candidates(src, sel, staging, 4096, (u64)p.g_tau[qg] << 32);
+  if (n <= (u32)RANK_SELECT_MAX) {
+    block_rank_select(staging, (int)n, p.top_k, sel);
+  } else if (n <= 4096u) {
+    CandidateLists ex;
+    ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n; ex.list_stride = 0; ex.count_stride = 0;
+    block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, 0.0);
+  } else {
+    block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, nullptr, nullptr, nullptr, nullptr, 0.0);
+  }
+  // sel.win[0..top_k): this query's winners, sorted (0 = empty).  Push them to every rank.
+  for (int i = threadIdx.x; i < p.top_k * px.world; i += blockDim.x) {
+    const int rr = i / p.top_k, j = i - rr * p.top_k;
+    const int peer = (px.rank + rr) % px.world;                  // own copy first, then round the ring
+    reinterpret_cast<u64*>(px.base[peer] + px.slot_off)[(long long)qg * p.top_k + j] = sel.win[j];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 ticket = atomicAdd(px.done, 1u);
+    last = ticket == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  if (threadIdx.x == 0) *px.done = 0;
+  __threadfence_system();
+  if ((int)threadIdx.x < px.world)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<u32*>(px.base[threadIdx.x]) +
+                                                            px.parity * MMF_XCHG_MAX_WORLD + px.rank), "r"(px.epoch) : "memory");
+}
+
 // Screened search, second half (VAR_SCREEN): one block per query.
 //   1. stage every candidate of the query whose APPROXIMATE score lies within the band below the grid-wide
 //      bound, and select the approximate top-k among them (block_select_topk, no outputs): its k-th entry T
@@ -1311,7 +1370,11 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
     mma_merge_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
                                                                   (u64*)out_packed, out_disc);
   } else {
-    if (fast)
+    if (fast && h->push_ctx && out_packed && !out_scores && !out_rows && !out_disc) {
+      // row-sharded search with the fused push: the winners go to every rank's gather buffer from this kernel
+      mma_merge_push_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, *h->push_ctx);
+      h->push_fused = true;
+    } else if (fast)
       mma_merge_kernel<KPL, CG, false, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores,
                                                                           (long long*)out_rows, (u64*)out_packed, out_disc);
     else

@@ -464,23 +464,28 @@ int main(int argc, char** argv) {
             if (rc != MMF_OK) { printf("warm-up search failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
           }
           CK(cudaDeviceSynchronize());
-          for (int rep = 0; rep < 3; ++rep) {       // 3 back-to-back exchanges: both parities + buffer reuse
+          for (int fused = 0; fused < 2; ++fused) {   // separate push kernel / push fused into the merge tail
+            setenv("MMF_EXCHANGE_FUSED", fused ? "1" : "0", 1);
+            for (int rep = 0; rep < 3; ++rep) {       // 3 back-to-back exchanges: both parities + buffer reuse
+              for (int r = 0; r < 2; ++r) {
+                int rc = mmf_vault_search_exchange(R[r], d_q, nq, k, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
+                if (rc != MMF_OK) { printf("search_exchange failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+              }
+            }
+            CK(cudaDeviceSynchronize());
             for (int r = 0; r < 2; ++r) {
-              int rc = mmf_vault_search_exchange(R[r], d_q, nq, k, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
-              if (rc != MMF_OK) { printf("search_exchange failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+              Result got;
+              got.scores.resize((size_t)nq * k); got.rows.resize((size_t)nq * k); got.disc.resize(nq);
+              CK(cudaMemcpy(got.scores.data(), sc[r], got.scores.size() * 4, cudaMemcpyDeviceToHost));
+              CK(cudaMemcpy(got.rows.data(), ro[r], got.rows.size() * 8, cudaMemcpyDeviceToHost));
+              CK(cudaMemcpy(got.disc.data(), di[r], got.disc.size() * 4, cudaMemcpyDeviceToHost));
+              char what[112];
+              snprintf(what, sizeof what, "%s k=%d %s rank %d%s", mode ? "bf16" : "fp32", k,
+                       algo == MMF_ALGO_MMA ? "tcgen05" : "stream", r, fused ? " (fused push requested)" : "");
+              fails += !same(got, full, nq, k, what);
             }
           }
-          CK(cudaDeviceSynchronize());
-          for (int r = 0; r < 2; ++r) {
-            Result got;
-            got.scores.resize((size_t)nq * k); got.rows.resize((size_t)nq * k); got.disc.resize(nq);
-            CK(cudaMemcpy(got.scores.data(), sc[r], got.scores.size() * 4, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(got.rows.data(), ro[r], got.rows.size() * 8, cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(got.disc.data(), di[r], got.disc.size() * 4, cudaMemcpyDeviceToHost));
-            char what[96];
-            snprintf(what, sizeof what, "%s k=%d %s rank %d", mode ? "bf16" : "fp32", k, algo == MMF_ALGO_MMA ? "tcgen05" : "stream", r);
-            fails += !same(got, full, nq, k, what);
-          }
+          unsetenv("MMF_EXCHANGE_FUSED");
         }
       }
     }
