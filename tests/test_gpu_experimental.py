@@ -196,3 +196,38 @@ def test_peer_exchange_single_rank_loopback(eng):
             eng.vault_search_exchange(np.zeros((100000, 512), np.float32), 100, 100)     # does not fit the attached buffer
     finally:
         eng.exchange_detach()
+
+
+def test_c4_shard_size_properties(eng):
+    """BASELINE config C4 at the size one rank sees on 8 GPUs (4096 queries x 1.25 M bf16 rows, top-100), through
+    size-independent properties: planted rows first at their cosine, scores sorted, a query scaled is the same
+    query, a 2-way row split + candidate merge equals the unsplit search bit for bit, both bound variants agree."""
+    n_rows, nq, k = 1_250_000, 4096, 100
+    g = torch.Generator(device="cuda").manual_seed(11)
+    vault = torch.randn(n_rows, 512, device="cuda", generator=g)
+    q = torch.randn(nq, 512, device="cuda", generator=g)
+    pick = torch.randint(0, n_rows, (400,), device="cuda", generator=g)
+    vn = torch.nn.functional.normalize(vault[pick], dim=1)
+    noise = torch.nn.functional.normalize(q[:400] - (q[:400] * vn).sum(1, keepdim=True) * vn, dim=1)
+    cosv = torch.tensor([0.8, 0.849, 0.851, 0.9, 0.99], device="cuda").repeat(80)
+    q[:400] = (cosv[:, None] * vn + torch.sqrt(1 - cosv ** 2)[:, None] * noise) * 3.0
+    eng.vault_load(vault, mode="bf16")
+    scores, rows, disc = eng.vault_search(q, k)
+    assert torch.equal(rows[:400, 0], pick)
+    assert torch.allclose(scores[:400, 0], cosv, atol=BF16_TOL)
+    safe = (cosv - 0.85).abs() > BF16_TOL
+    assert torch.equal((disc[:400] > 0)[safe], (cosv > 0.85)[safe])
+    assert torch.all(scores[:, :-1] >= scores[:, 1:]) and torch.all(rows >= 0)
+    s2, r2, _ = eng.vault_search(q * 0.01, k)
+    assert torch.equal(r2, rows) and torch.equal(s2, scores)          # the bf16 operand of q/|q| does not depend on |q| ... up to fp32 rounding
+    with env(MMF_MMA_BOUND="pool"):
+        s3, r3, d3 = eng.vault_search(q, k)
+    assert torch.equal(r3, rows) and torch.equal(s3, scores) and torch.equal(d3, disc)
+    half = n_rows // 2
+    packed = []
+    for lo, hi in ((0, half), (half, n_rows)):
+        eng.vault_load(vault[lo:hi], mode="bf16", row_offset=lo)
+        packed.append(eng.vault_search_candidates(q, k).clone())
+    s4, r4, d4 = eng.topk_merge(torch.stack(packed), k)
+    assert torch.equal(r4, rows) and torch.equal(s4, scores) and torch.equal(d4, disc)
+    eng.vault_unload()
