@@ -14,9 +14,17 @@
 //   * B = vault rows, K-major 128B-swizzled [rows][64] tiles streamed by TMA through an mbarrier ring
 //       (bf16: 8 stages x 2 k-blocks x 8 KB per CTA; fp32-exact: 6 x (vh + vl = 16 KB) next to ql).
 //   MMF_VAULT_BF16: D += q.v, 4 TS-UMMA (K=16) per 64-wide k-block.
-//   MMF_VAULT_FP32: fp32-exact.  x*2^8 = hi + lo (two fp16 planes, 22+ bits), and
-//       q.v * 2^16 = qh.vh + qh.vl + ql.vh  (+ ql.vl, < 2^-22 relative, dropped)
-//     -> 8 TS + 4 SS UMMA per k-block, all into ONE fp32 TMEM accumulator; scores = D * 2^-16.
+//   MMF_VAULT_FP32: fp32-exact.  x*2^8 = hi + lo (two fp16 planes, 22+ bits).
+//     top_k <= 16 (the reference's use: k = 5 / 10): SCREENED search (VAR_SCREEN).  One pass
+//       qh.vh over the hi planes -- the bf16-shaped pipeline on fp16 data, TMA fetches only the first 1 KB of each
+//       2 KB row -- is within a proven eps of the exact score; every element within 2*eps of the running k-th best
+//       survives, mma_rerank_kernel re-scores the survivors exactly (fp32, from hi+lo, the streaming kernel's
+//       arithmetic) and selects the top-k among them.  A third of the MMA work and half of the DRAM bytes of the
+//       3-pass form; results bit-identical to the streaming kernel.  Bands that do not fit set a flag and the
+//       guarded 3-pass kernel (VAR_GUARD, launched after every screened search, returns at once otherwise) redoes
+//       the batch.
+//     top_k > 16: three passes,  q.v * 2^16 = qh.vh + qh.vl + ql.vh  (+ ql.vl, < 2^-22 relative, dropped)
+//       -> 8 TS + 4 SS UMMA per k-block, all into ONE fp32 TMEM accumulator; scores = D * 2^-16.
 //   * L2-aware schedule (pair_schedule): the pairs working on different query-tile groups sweep the
 //     same vault segment together, so a vault tile is fetched from DRAM by one and hit in L2 by the rest.
 //
@@ -33,14 +41,20 @@
 // threshold (a lower bound of its k-th best) and appends the rare survivors to its candidate list in
 // global memory (L2-resident).  Thresholds: exact for top_k <= 16 (the best values sorted in
 // registers), otherwise refreshed when a list is compacted (whole warp, topk.cuh); in both cases
-// tightened grid-wide through a pool of bucket maxima (pool[row % buckets]: >= top_k distinct rows, so
-// the minimum over the buckets bounds the k-th best from below).  A block works on "strips" (one group
-// of query tiles x a run of vault tiles) so that state stays in registers; a merge kernel selects the
-// final top-k per query from the strips' lists.
+// tightened grid-wide: top_k <= 16 through a pool of bucket maxima (pool[row % buckets]: >= top_k distinct
+// rows, so the minimum over the buckets bounds the k-th best from below), top_k > 16 through a per-query
+// HISTOGRAM of candidate scores (VAR_HIST: the lower edge of the bin holding the k-th best counted candidate;
+// the bucket minimum sits near rank k*H(k), the histogram edge near rank 1.4*k).  A block works on "strips"
+// (one group of query tiles x a run of vault tiles) so that state stays in registers; a tail kernel
+// (mma_merge_kernel / mma_rerank_kernel: parallel slot gather, one staging sweep, rank-by-counting or radix
+// select) produces the final top-k per query from the strips' lists.
 //
-// Triage switches (never needed in production): env MMF_MMA_DEBUG (bit 0: skip the filter, 1: skip
-// the vault TMA, 2: skip the MMA warp's waits, 3: print in-kernel cycle counts), MMF_MMA_CG (force 1
-// or 2 CTAs per MMA), MMF_MMA_FLAT (plain flattened schedule instead of the L2-aware one).
+// Switches (environment, read per search; never needed in production -- INTEGRATION.md has the table):
+// MMF_MMA_SCREEN=0 (3-pass instead of screened), MMF_MMA_BOUND=pool (bucket maxima instead of the histogram),
+// MMF_MERGE_FAST=0 (first form of the tails); experiments not yet run on a GPU: MMF_MMA_STAGES=12, MMF_MMA_PREFETCH=1,
+// MMF_MMA_LEAN=1; triage: MMF_MMA_DEBUG (bit 0: skip the filter, 1: skip the vault TMA, 2: skip the MMA warp's
+// waits, 3: print in-kernel cycle counts), MMF_MMA_CG (force 1 or 2 CTAs per MMA), MMF_MMA_FLAT (plain
+// flattened schedule instead of the L2-aware one).
 #include "common.cuh"
 #include "topk.cuh"
 
