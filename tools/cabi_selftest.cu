@@ -229,6 +229,20 @@ int main(int argc, char** argv) {
            rows_fp32 * 2048.0 / ms_lean * 1e-6);
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
+    // batch-1 latency path (C3): exact streaming kernel vs its screened variant, 1 and 8 queries
+    for (int nqs = 1; nqs <= 8; nqs *= 8) {
+      float ms_exact = 0, ms_scr = 0;
+      unsetenv("MMF_STREAM_SCREEN");
+      Result ex1 = search(nqs, k, MMF_ALGO_STREAM, &ms_exact, 20);
+      setenv("MMF_STREAM_SCREEN", "1", 1);
+      Result sc1 = search(nqs, k, MMF_ALGO_STREAM, &ms_scr, 20);
+      unsetenv("MMF_STREAM_SCREEN");
+      char what[96];
+      snprintf(what, sizeof what, "screened streaming kernel vs exact, %d quer%s", nqs, nqs == 1 ? "y" : "ies");
+      fails += !same(sc1, ex1, nqs, k, what);
+      printf("  batch-%d search: exact %.3f ms (%.0f GB/s), screened (MMF_STREAM_SCREEN=1) %.3f ms (%.0f GB/s algorithmic)\n", nqs,
+             ms_exact, rows_fp32 * 2048.0 / ms_exact * 1e-6, ms_scr, rows_fp32 * 2048.0 / ms_scr * 1e-6);
+    }
     // band overflow: 3000 identical rows -> guarded 3-pass redo, ties by row id
     duplicate_rows<<<(unsigned)((3000ll * 512 + 255) / 256), 256>>>(d_vault, 5, 70000, 73000);
     CK(cudaMemcpy(d_q, d_vault + 5 * 512, 512 * 4, cudaMemcpyDeviceToDevice));   // query 0 = the duplicated row
@@ -247,6 +261,16 @@ int main(int argc, char** argv) {
     unsetenv("MMF_MMA_SCREEN");
     fails += !same(lean2, mma2, nq, k, "lean sequence, overflowing band vs 3-pass");
     fails += !same(lean3, mma2, nq, k, "lean sequence, overflowing band, second call");
+    {
+      unsetenv("MMF_STREAM_SCREEN");
+      Result ex2 = search(8, k, MMF_ALGO_STREAM);
+      setenv("MMF_STREAM_SCREEN", "1", 1);
+      Result sc2 = search(8, k, MMF_ALGO_STREAM);
+      Result sc3 = search(8, k, MMF_ALGO_STREAM);       // twice: flag and bounds of the guarded pass must reset
+      unsetenv("MMF_STREAM_SCREEN");
+      fails += !same(sc2, ex2, 8, k, "screened streaming kernel, overflowing band vs exact");
+      fails += !same(sc3, ex2, 8, k, "screened streaming kernel, overflowing band, second call");
+    }
     printf("  query 0 top rows: %lld %lld %lld (expect 72999 72998 72997)\n", (long long)screen2.rows[0],
            (long long)screen2.rows[1], (long long)screen2.rows[2]);
     fails += screen2.rows[0] != 72999;
@@ -321,6 +345,12 @@ int main(int argc, char** argv) {
         fails += !same(fast, var, sh.nq, sh.k, what_fast);
         if (mode == 0 && sh.k <= 16) {
           Result stream = search(sh.nq, sh.k, MMF_ALGO_STREAM);
+          if (sh.nq <= 64) {                         // the streaming kernel's own screened variant (small batches)
+            setenv("MMF_STREAM_SCREEN", "1", 1);
+            Result sscr = search(sh.nq, sh.k, MMF_ALGO_STREAM);
+            unsetenv("MMF_STREAM_SCREEN");
+            fails += !same(sscr, stream, sh.nq, sh.k, "   MMF_STREAM_SCREEN=1 vs exact streaming kernel");
+          }
           fails += !same(var, stream, sh.nq, sh.k, what);
           fails += !near_equal(base, stream, sh.nq, sh.k, 1e-5f, "   (3-pass vs streaming kernel)");
         } else {
