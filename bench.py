@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--rows", type=int, default=0, help="override vault rows (debug only; the line then says so)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="additionally capture one step (device-resident inputs) in a CUDA graph and report its replay time "
+                         "under \"graph\" (additive: the headline numbers are measured without it; not yet run on a GPU)")
     ap.add_argument("--e2e-api", default="tensors", choices=["tensors", "host"],
                     help="e2e leg: mmf_b200.score_batch on pinned tensors + .cpu() per result (default), or the single "
                          "host-buffer library call Engine.score_batch_host (not yet validated on a GPU)")
@@ -314,6 +317,33 @@ def main():
     h2d = text_host.numel() * 4 + img_host.numel() * 4 + head_host.numel() * 4
     d2h = sum(t.numel() * t.element_size() for t in res)
 
+    # optional: the same step as a CUDA graph (fixed shapes, static buffers): what the launch gaps cost
+    graph_info = None
+    if args.graph and not sharded:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step_device()                           # scratch growth etc. must happen before the capture
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            graph_out = step_device()
+        for _ in range(args.warmup):
+            cg.replay()
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(args.steps):
+            cg.replay()
+        g1.record()
+        torch.cuda.synchronize()
+        graph_ms = g0.elapsed_time(g1) / args.steps
+        ok = torch.equal(graph_out["vault_rows"][:n_plant, 0].cpu(), pick + (0 if sharded else lo))
+        graph_info = {"ms_per_step": graph_ms, "value": Q / (graph_ms * 1e-3), "unit": "queries/s (this rank)",
+                      "planted_rows_recovered": bool(ok)}
+
     # batch-1 latency mode: distribution over 1000 DISTINCT queries, one search each, device-timed
     latency = None
     if args.workload == "c3" and world == 1:
@@ -436,6 +466,8 @@ def main():
         }
         if latency is not None:
             line["latency"] = latency
+        if graph_info is not None:
+            line["graph"] = graph_info
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -23,7 +23,7 @@ MMF_EXPERIMENTAL=1 run 600 pytest_experimental.log python -m pytest tests/test_g
 tail -3 gpurun_out/pytest_experimental.log
 # 4. bench lines: default workload with both e2e paths, batch-1 latency mode, 10M-row bf16 on one GPU
 run 300 bench_c2.json python bench.py
-run 200 bench_c2_e2e_host.json python bench.py --e2e-api host --no-cpu-baseline
+run 200 bench_c2_e2e_host.json python bench.py --e2e-api host --graph --no-cpu-baseline
 run 200 bench_c3.json python bench.py --workload c3 --no-cpu-baseline
 run 400 bench_c4_n1.json python bench.py --workload c4 --no-cpu-baseline --steps 10
 run 120 bench_reference.json python bench.py --impl reference --steps 5 --warmup 1
