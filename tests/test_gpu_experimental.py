@@ -232,3 +232,51 @@ def test_c4_shard_size_properties(eng):
     s4, r4, d4 = eng.topk_merge(torch.stack(packed), k)
     assert torch.equal(r4, rows) and torch.equal(s4, scores) and torch.equal(d4, disc)
     eng.vault_unload()
+
+
+# ------------------------------------------------------------------------------ variants written without a GPU at hand
+@pytest.mark.parametrize("n_rows,nq,k", [(1, 1, 1), (31, 3, 5), (1000, 1, 10), (4099, 2, 7), (20000, 5, 10), (70001, 15, 5),
+                                         (300000, 8, 16), (1_000_000, 1, 10)])
+def test_screened_streaming_kernel_is_exact(eng, n_rows, nq, k):
+    """MMF_STREAM_SCREEN=1 (batch-1 path reads only the hi planes, re-scores the band exactly) == exact streaming kernel"""
+    g = torch.Generator(device="cuda").manual_seed(n_rows + nq)
+    vault = torch.randn(n_rows, 512, device="cuda", generator=g) * (0.1 + torch.rand(n_rows, 1, device="cuda", generator=g) * 4)
+    q = torch.randn(nq, 512, device="cuda", generator=g)
+    q[0] = vault[n_rows // 2] * 2 + 0.3 * q[0]
+    eng.vault_load(vault, mode="fp32")
+    want = [npy(t) for t in eng.vault_search(q, k, algo="stream")]
+    with env(MMF_STREAM_SCREEN="1"):
+        got = [npy(t) for t in eng.vault_search(q, k, algo="stream")]
+        again = [npy(t) for t in eng.vault_search(q, k, algo="stream")]
+    for a, b, c in zip(got, want, again):
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(c, b, equal_nan=True)
+
+
+def test_screened_streaming_kernel_overflow_and_ties(eng):
+    base = synth.vault_rows(20000, seed=61)
+    vault = np.concatenate([base[:5000], np.repeat(base[7:8], 4000, axis=0), base[5000:]])
+    q = np.stack([base[7] * 2.0, base[9], base[11] + 0.1 * base[12]])
+    eng.vault_load(vault, mode="fp32")
+    want = [npy(t) for t in eng.vault_search(q, 10, algo="stream")]
+    with env(MMF_STREAM_SCREEN="1"):
+        got = [npy(t) for t in eng.vault_search(q, 10, algo="stream")]
+    assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, want))
+    assert list(got[1][0]) == list(range(8999, 8989, -1))
+
+
+@pytest.mark.parametrize("switches", [{"MMF_MMA_STAGES": "12"}, {"MMF_MMA_PREFETCH": "1"}, {"MMF_MMA_LEAN": "1"},
+                                      {"MMF_MMA_STAGES": "12", "MMF_MMA_PREFETCH": "1", "MMF_MMA_LEAN": "1"}])
+def test_screened_search_experiments_change_nothing(eng, switches):
+    """deeper ring / L2 prefetch / lean launch sequence only change HOW the screening pass runs"""
+    for n_rows, nq, k in ((40000, 257, 10), (5000, 16, 10), (500000, 256, 5)):
+        g = torch.Generator(device="cuda").manual_seed(n_rows)
+        vault = torch.randn(n_rows, 512, device="cuda", generator=g)
+        q = torch.randn(nq, 512, device="cuda", generator=g)
+        q[:8] = vault[:8] + 0.2 * q[:8]
+        eng.vault_load(vault, mode="fp32")
+        want = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+        with env(**switches):
+            got = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+            again = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+        for a, b, c in zip(got, want, again):
+            assert np.array_equal(a, b, equal_nan=True) and np.array_equal(c, b, equal_nan=True), (switches, n_rows)
