@@ -132,8 +132,17 @@ int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n
 int mmf_exchange_layout(int world, int64_t n_queries, int k_in, int64_t* gather_bytes_per_parity, int64_t* bytes_needed);
 int mmf_exchange_attach(mmf_handle* h, int rank, int world, const uint64_t* peer_ptrs, int64_t bytes_per_rank);
 int mmf_exchange_detach(mmf_handle* h);
-/* Local search (k_local = min(top_k, rows per rank) candidates per query) + push + wait + merge.  Outputs as
- * mmf_vault_search, identical on every rank; asynchronous on `stream`. */
+/* The two phases of an exchange, for callers that want to put other work between them (and for single-device
+ * checks, which must enqueue every rank's push before any rank's merge -- see csrc/exchange.cu):
+ * mmf_vault_search_push: local search (k_local candidates per query) + push into every rank's buffer + flag;
+ * never waits.  mmf_vault_exchange_merge: device-side wait for all ranks' candidates of the pending exchange +
+ * merge into the global top_k (top_k >= k_local).  One exchange may be pending per handle. */
+int mmf_vault_search_push(mmf_handle* h, const float* queries, int64_t n_queries, int k_local, int algo,
+                          mmf_stream_t stream);
+int mmf_vault_exchange_merge(mmf_handle* h, int top_k, double threshold, float* out_scores, int64_t* out_rows,
+                             float* out_discrepancy, mmf_stream_t stream);
+/* Both phases in one call: local search (k_local = min(top_k, rows per rank) candidates per query) + push +
+ * wait + merge.  Outputs as mmf_vault_search, identical on every rank; asynchronous on `stream`. */
 int mmf_vault_search_exchange(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int k_local,
                               double threshold, int algo, float* out_scores, int64_t* out_rows,
                               float* out_discrepancy, mmf_stream_t stream);

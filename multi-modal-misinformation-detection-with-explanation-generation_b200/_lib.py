@@ -33,6 +33,8 @@ SIGNATURES = {
     "mmf_exchange_layout": (_i, [_i, _l, _i, C.POINTER(_l), C.POINTER(_l)]),
     "mmf_exchange_attach": (_i, [_p, _i, _i, C.POINTER(C.c_uint64), _l]),
     "mmf_exchange_detach": (_i, [_p]),
+    "mmf_vault_search_push": (_i, [_p, _p, _l, _i, _i, _p]),
+    "mmf_vault_exchange_merge": (_i, [_p, _i, _d, _p, _p, _p, _p]),
     "mmf_vault_search_exchange": (_i, [_p, _p, _l, _i, _i, _d, _i, _p, _p, _p, _p]),
     "mmf_fusion_load": (_i, [_p, _p]),
     "mmf_fusion_forward": (_i, [_p, _p, _l, _p, _p, _p, _p]),

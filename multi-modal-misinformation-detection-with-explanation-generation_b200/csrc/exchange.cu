@@ -26,7 +26,10 @@
 // order -- so two buffers are enough and no back-signal is needed.
 //
 // Progress: a push never waits, and every rank enqueues its push before its wait-merge, so the spinning
-// blocks of the wait-merge kernel cannot keep a needed kernel off the device.
+// blocks of the wait-merge kernel cannot keep a needed kernel off the device -- PROVIDED every rank has its own
+// GPU.  Never run two ranks of this protocol on one device at the same time (nothing guarantees that the kernel
+// that is waited for gets to run; B200_PROFILING.md reports Xid 109 for that pattern): the single-device checks
+// (tools/cabi_selftest, tests) enqueue ALL pushes before ANY merge on one stream, so no kernel ever waits.
 //
 // STATUS: compiles for sm_100a; NOT yet run on a multi-GPU box (written after the round's GPU time was spent).
 // Off by default: TruthVault(exchange="p2p") / MMF_EXCHANGE=p2p selects it, the NCCL all-gather stays the default.
@@ -57,6 +60,9 @@ struct ExchangeState {
   u64* local = nullptr;                         // this rank's packed candidates of the current call
   size_t local_bytes = 0;
   u32* done = nullptr;                          // ticket counter of the push kernel (device, self-resetting)
+  int64_t pending_queries = 0;                  // > 0 between mmf_vault_search_push and mmf_vault_exchange_merge
+  int pending_k = 0;
+  size_t pending_gather_off = 0;
 };
 
 __device__ __forceinline__ void st_release_sys(u32* p, u32 v) {
@@ -162,6 +168,7 @@ extern "C" int mmf_exchange_attach(mmf_handle* h, int rank, int world, const uin
   x->world = world;
   x->bytes_per_rank = (size_t)bytes_per_rank;
   x->epoch = 0;
+  x->pending_queries = 0;
   // this rank's candidates of one exchange can never exceed one slot of the attached buffer: size the local
   // buffer for that now, so that the (asynchronous) search path never allocates or synchronises
   const size_t local_cap = ((size_t)bytes_per_rank - MMF_XCHG_HEADER) / 2 / (size_t)world + 1024;
@@ -193,33 +200,34 @@ extern "C" int mmf_exchange_detach(mmf_handle* h) {
   return MMF_OK;
 }
 
-extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int k_local,
-                                         double threshold, int algo, float* out_scores, int64_t* out_rows,
-                                         float* out_discrepancy, mmf_stream_t stream) {
+// Phase 1 of an exchange: local search of this rank's shard + push of its candidates into every rank's gather
+// buffer + publication of this rank's epoch flag.  Never waits for anybody.  Asynchronous on `stream`.
+extern "C" int mmf_vault_search_push(mmf_handle* h, const float* queries, int64_t n_queries, int k_local, int algo,
+                                     mmf_stream_t stream) {
   if (!h) return MMF_ERR_BAD_ARG;
   ExchangeState* x = (ExchangeState*)h->xchg_state;
-  if (!x) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_search_exchange: no peer buffers attached");
-  if (n_queries < 0 || top_k < 1 || top_k > MMF_MAX_TOP_K || k_local < 1 || k_local > top_k ||
-      (n_queries > 0 && (!queries || !out_scores || !out_rows)))
-    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_exchange: bad argument (n_queries=%lld top_k=%d k_local=%d)",
-                         (long long)n_queries, top_k, k_local);
-  if (n_queries == 0) return MMF_OK;
+  if (!x) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_search_push: no peer buffers attached");
+  if (n_queries <= 0 || k_local < 1 || k_local > MMF_MAX_TOP_K || !queries)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_push: bad argument (n_queries=%lld k_local=%d)",
+                         (long long)n_queries, k_local);
+  if (x->pending_queries != 0)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_push: the previous exchange has not been merged yet");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t per_parity = 0, need = 0;
   mmf_exchange_layout(x->world, n_queries, k_local, &per_parity, &need);
   if ((size_t)need > x->bytes_per_rank)
-    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: %lld bytes of peer buffer needed, %zu attached",
+    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_push: %lld bytes of peer buffer needed, %zu attached",
                          (long long)need, x->bytes_per_rank);
   const size_t local_bytes = (size_t)n_queries * k_local * 8;
   if (local_bytes > x->local_bytes)      // cannot happen after the size check above (attach sized it for one slot)
-    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_exchange: local candidate buffer too small");
-  const u32 epoch = ++x->epoch;
+    return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_push: local candidate buffer too small");
+  const u32 epoch = x->epoch + 1;
   const int parity = (int)(epoch & 1u);
   const size_t gather_off = MMF_XCHG_HEADER + (size_t)parity * (size_t)per_parity;
   const size_t slot_off = gather_off + (size_t)x->rank * local_bytes;
-  // 1. local search of this rank's shard -> packed candidates with GLOBAL row ids.
-  //    MMF_EXCHANGE_FUSED=1 (experimental): the search writes them into this rank's own slot and, where its merge
-  //    tail supports it (tcgen05 search, top_k > 16), pushes them to the peers and publishes the flags itself.
+  // local search of this rank's shard -> packed candidates with GLOBAL row ids.
+  // MMF_EXCHANGE_FUSED=1 (experimental): the search writes them into this rank's own slot and, where its merge
+  // tail supports it (tcgen05 search, top_k > 16), pushes them to the peers and publishes the flags itself.
   bool want_fused = false;
   { const char* e = getenv("MMF_EXCHANGE_FUSED"); want_fused = e && atoi(e) != 0 && n_queries <= 65536; }
   mmf_push_ctx ctx;
@@ -229,19 +237,51 @@ extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, in
   u64* packed = want_fused ? reinterpret_cast<u64*>(x->peers.base[x->rank] + slot_off) : x->local;
   h->push_fused = false;
   h->push_ctx = want_fused ? &ctx : nullptr;
-  int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)packed, st, "vault_search_exchange");
+  int rc = mmf_search_dispatch_packed(h, queries, n_queries, k_local, algo, (uint64_t*)packed, st, "vault_search_push");
   h->push_ctx = nullptr;
   if (rc != MMF_OK) return rc;
-  // 2. push into every rank's gather buffer + publish (unless the search's tail already did), 3. wait + merge
   if (!h->push_fused) {
     const long long n = (long long)n_queries * k_local;
     const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)h->sm_count * 4);
     exchange_push_kernel<<<blocks, 256, 0, st>>>(packed, n, x->peers, x->rank, x->world, slot_off, parity, epoch, x->done);
     MMF_LAUNCH_OK(h);
   }
-  exchange_wait_merge_kernel<<<(unsigned)n_queries, 256, 0, st>>>(x->peers.base[x->rank], x->world, gather_off, parity, epoch,
-                                                                 (long long)n_queries, k_local, top_k, threshold, out_scores,
-                                                                 (long long*)out_rows, out_discrepancy);
+  x->epoch = epoch;
+  x->pending_queries = n_queries;
+  x->pending_k = k_local;
+  x->pending_gather_off = gather_off;
+  return MMF_OK;
+}
+
+// Phase 2: wait (on the device) until every rank's candidates of the pending exchange have landed, merge them.
+extern "C" int mmf_vault_exchange_merge(mmf_handle* h, int top_k, double threshold, float* out_scores, int64_t* out_rows,
+                                        float* out_discrepancy, mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  ExchangeState* x = (ExchangeState*)h->xchg_state;
+  if (!x) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_exchange_merge: no peer buffers attached");
+  if (x->pending_queries == 0) return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_exchange_merge: no exchange pending");
+  if (top_k < x->pending_k || top_k > MMF_MAX_TOP_K || !out_scores || !out_rows)
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_exchange_merge: bad argument (top_k=%d, %d candidates per rank)", top_k,
+                         x->pending_k);
+  const int64_t n_queries = x->pending_queries;
+  exchange_wait_merge_kernel<<<(unsigned)n_queries, 256, 0, (cudaStream_t)stream>>>(
+      x->peers.base[x->rank], x->world, x->pending_gather_off, (int)(x->epoch & 1u), x->epoch, (long long)n_queries, x->pending_k,
+      top_k, threshold, out_scores, (long long*)out_rows, out_discrepancy);
+  x->pending_queries = 0;
   MMF_LAUNCH_OK(h);
   return MMF_OK;
+}
+
+extern "C" int mmf_vault_search_exchange(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, int k_local,
+                                         double threshold, int algo, float* out_scores, int64_t* out_rows,
+                                         float* out_discrepancy, mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n_queries < 0 || top_k < 1 || top_k > MMF_MAX_TOP_K || k_local < 1 || k_local > top_k ||
+      (n_queries > 0 && (!queries || !out_scores || !out_rows)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_exchange: bad argument (n_queries=%lld top_k=%d k_local=%d)",
+                         (long long)n_queries, top_k, k_local);
+  if (n_queries == 0) return MMF_OK;
+  const int rc = mmf_vault_search_push(h, queries, n_queries, k_local, algo, stream);
+  if (rc != MMF_OK) return rc;
+  return mmf_vault_exchange_merge(h, top_k, threshold, out_scores, out_rows, out_discrepancy, stream);
 }

@@ -447,17 +447,18 @@ int main(int argc, char** argv) {
     printf("  end to end, pinned host buffers, %d queries x %lld rows: %.3f ms per call (%.0f queries/s)\n", nq, n, ms, nq / ms * 1e3);
     cudaFreeHost(pin); cudaFree(d_text); cudaFree(d_sim); cudaFree(d_x); cudaFree(d_p);
   }
-  // ---------------- peer-memory candidate exchange (csrc/exchange.cu): 2 ranks emulated on ONE device
-  // (two handles, two streams, two buffers of this device).  Small query counts only: on one GPU the spinning
-  // wait-merge blocks of "rank 0" must leave room for the kernels of "rank 1" (on real ranks they cannot collide).
+  // ---------------- peer-memory candidate exchange (csrc/exchange.cu): the protocol of 2 ranks on ONE device.
+  // Kernels that wait for one another must never share a GPU (nothing guarantees that the one waited for runs;
+  // B200_PROFILING.md: Xid 109), so both "ranks" use ONE stream and every exchange is enqueued as
+  // push(rank 0), push(rank 1), merge(rank 0), merge(rank 1): when a merge kernel starts, all flags are already
+  // set and nothing ever spins.  What this checks: slot layout, flags, epochs / parities, the merge itself.
   {
-    printf("[exchange] 2 emulated ranks vs the unsharded search\n");
+    printf("[exchange] 2 ranks' protocol, phases in sequence on one stream, vs the unsharded search\n");
     mmf_handle* R[2] = {nullptr, nullptr};
-    cudaStream_t S[2];
-    for (int r = 0; r < 2; ++r) {
+    cudaStream_t S;
+    CK(cudaStreamCreateWithFlags(&S, cudaStreamNonBlocking));
+    for (int r = 0; r < 2; ++r)
       if (mmf_create(0, &R[r]) != MMF_OK) { printf("mmf_create failed\n"); return 1; }
-      CK(cudaStreamCreateWithFlags(&S[r], cudaStreamNonBlocking));
-    }
     const long long n = 200001;
     const int nq = 24;
     int64_t need = 0;
@@ -487,19 +488,16 @@ int main(int argc, char** argv) {
         const int k = ks[t];
         for (int algo = MMF_ALGO_STREAM; algo <= MMF_ALGO_MMA; ++algo) {
           Result full = search(nq, k, algo);
-          // one process plays both ranks here: anything that synchronises the DEVICE between enqueueing rank 0 and
-          // rank 1 (scratch growth on a first call) would wait for rank 0's spinning merge forever -> warm up first
-          for (int r = 0; r < 2; ++r) {
-            int rc = mmf_vault_search(R[r], d_q, nq, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
-            if (rc != MMF_OK) { printf("warm-up search failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
-          }
-          CK(cudaDeviceSynchronize());
           for (int fused = 0; fused < 2; ++fused) {   // separate push kernel / push fused into the merge tail
             setenv("MMF_EXCHANGE_FUSED", fused ? "1" : "0", 1);
-            for (int rep = 0; rep < 3; ++rep) {       // 3 back-to-back exchanges: both parities + buffer reuse
+            for (int rep = 0; rep < 3; ++rep) {       // 3 exchanges in a row: both parities + buffer reuse
               for (int r = 0; r < 2; ++r) {
-                int rc = mmf_vault_search_exchange(R[r], d_q, nq, k, k, 0.85, algo, sc[r], ro[r], di[r], S[r]);
-                if (rc != MMF_OK) { printf("search_exchange failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+                int rc = mmf_vault_search_push(R[r], d_q, nq, k, algo, S);
+                if (rc != MMF_OK) { printf("search_push failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
+              }
+              for (int r = 0; r < 2; ++r) {
+                int rc = mmf_vault_exchange_merge(R[r], k, 0.85, sc[r], ro[r], di[r], S);
+                if (rc != MMF_OK) { printf("exchange_merge failed on rank %d: %s\n", r, mmf_last_error(R[r])); return 1; }
               }
             }
             CK(cudaDeviceSynchronize());
@@ -519,7 +517,8 @@ int main(int argc, char** argv) {
         }
       }
     }
-    for (int r = 0; r < 2; ++r) { mmf_destroy(R[r]); cudaFree(B[r]); cudaFree(sc[r]); cudaFree(ro[r]); cudaFree(di[r]); cudaStreamDestroy(S[r]); }
+    for (int r = 0; r < 2; ++r) { mmf_destroy(R[r]); cudaFree(B[r]); cudaFree(sc[r]); cudaFree(ro[r]); cudaFree(di[r]); }
+    cudaStreamDestroy(S);
   }
   printf("launches: %lld; %s\n", (long long)mmf_launch_count(H), fails ? "SELFTEST FAILED" : "selftest ok");
   mmf_destroy(H);

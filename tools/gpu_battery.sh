@@ -32,8 +32,14 @@ for f in bench_c2 bench_c2_e2e_host bench_c3 bench_c4_n1 bench_c5; do tail -c 12
 # 5. A/B of the experiments through the Python API
 run 300 ab_experimental.log python tools/ab_experimental.py
 cat gpurun_out/ab_experimental.log
-# 6. ncu: launch list of the default bench command, full capture of the dominant kernels (after everything passed)
-run 300 ncu_launches.log ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
-  --log-file gpurun_out/c2_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline
-run 200 ncu_full.log ncu --set full --clock-control none --import-source on -k regex:vault_mma_topk -c 3 -f \
-  -o gpurun_out/c2_c4shard_full tools/cabi_selftest profile
+# 6. ncu (B200_PROFILING.md: only after the SAME command line has exited 0 without ncu, `&&` directly before it):
+#    launch list of the default bench command, full capture of the dominant kernels
+echo "=== ncu launch list + full capture"
+timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_plain_bench.log 2>&1 &&
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+  --log-file gpurun_out/c2_launches_ncu.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+echo "    rc=$?"
+timeout 60 tools/cabi_selftest profile > gpurun_out/ncu_plain_selftest.log 2>&1 &&
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:vault_mma_topk -c 3 -f \
+  -o gpurun_out/c2_c4shard_full tools/cabi_selftest profile > gpurun_out/ncu_full.log 2>&1
+echo "    rc=$?"
