@@ -105,6 +105,27 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_info():
+    """CPU model / thread count / BLAS of the box the CPU baseline ran on; best effort, never raises."""
+    info = {}
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    info["cpu_model"] = line.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    try:
+        info["torch_threads"] = int(torch.get_num_threads())
+        info["blas"] = "mkl" if torch.backends.mkl.is_available() else "not mkl"
+        info["numpy"] = np.__version__
+        info["torch"] = torch.__version__
+    except Exception:
+        pass
+    return info
+
+
 def dist_env():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
@@ -163,7 +184,7 @@ def run_reference_arm(args, wl):
                    "dim": 512, "top_k": k, "vault_mode": wl["mode"], "algo": "reference as shipped (NumPy, per-query renormalisation)",
                    "parallelism": "host CPU, %d cores (BLAS threads)" % cores,
                    "sample": "each step = %d query of the workload's %d-query batch against the full vault" % (n_sample, wl["q"])},
-        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample, "host": host_info()},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -443,6 +464,7 @@ def main():
         cpu["batched_restatement"] = {"value": Q / dtb, "unit": "queries/s", "threads": torch.get_num_threads(),
                                       "sample": f"all {Q} queries vs {sub} vault rows, time scaled to {n_local} rows; "
                                                 "normalise once + Qn@Vn.T + torch.topk"}
+        cpu["host"] = host_info()
         del vault_host, vn
 
     if rank == 0:
