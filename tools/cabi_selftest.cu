@@ -34,6 +34,23 @@
 
 static mmf_handle* H = nullptr;
 
+// Section / arm selection, so that a crash in an arm that has never run on a GPU cannot hide the others:
+//   SELFTEST_ONLY=a,b   run only these (the baselines they compare against always run)
+//   SELFTEST_SKIP=a,b   run everything but these
+// tokens: deep prefetch lean streamscreen bf16 sweep host exchange
+static bool in_list(const char* list, const char* tok) {
+  if (!list) return false;
+  const size_t n = strlen(tok);
+  for (const char* p = list; (p = strstr(p, tok)) != nullptr; p += n)
+    if ((p == list || p[-1] == ',') && (p[n] == 0 || p[n] == ',')) return true;
+  return false;
+}
+static bool want(const char* tok) {
+  const char* only = getenv("SELFTEST_ONLY");
+  if (only && *only) return in_list(only, tok);
+  return !in_list(getenv("SELFTEST_SKIP"), tok);
+}
+
 __device__ __forceinline__ uint32_t hash32(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
   return (uint32_t)x;
@@ -190,6 +207,7 @@ int main(int argc, char** argv) {
     setenv("MMF_MMA_SCREEN", "0", 1);
     fails += !same(fast, stream, nq, k, "screened search + fast tail vs streaming kernel");
     printf("  search time with MMF_MERGE_FAST=1: %.3f ms (%.0f GB/s algorithmic)\n", ms_fast, rows_fp32 * 2048.0 / ms_fast * 1e-6);
+    if (want("deep")) {
     float ms_deep = 0;
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
@@ -201,6 +219,8 @@ int main(int argc, char** argv) {
     fails += !same(deep, stream, nq, k, "screened search, 12-stage ring vs streaming kernel");
     printf("  search time with MMF_MMA_STAGES=12 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_deep,
            rows_fp32 * 2048.0 / ms_deep * 1e-6);
+    }
+    if (want("prefetch")) {
     float ms_pref = 0, ms_both = 0;
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
@@ -216,6 +236,8 @@ int main(int argc, char** argv) {
     fails += !same(both, stream, nq, k, "screened search, L2 prefetch + 12-stage ring");
     printf("  search time with MMF_MMA_PREFETCH=1: %.3f ms (%.0f GB/s algorithmic); + MMF_MMA_STAGES=12: %.3f ms (%.0f GB/s)\n",
            ms_pref, rows_fp32 * 2048.0 / ms_pref * 1e-6, ms_both, rows_fp32 * 2048.0 / ms_both * 1e-6);
+    }
+    if (want("lean")) {
     float ms_lean = 0;
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MERGE_FAST", "1", 1);
@@ -227,10 +249,11 @@ int main(int argc, char** argv) {
     fails += !same(lean, stream, nq, k, "screened search, lean launch sequence vs streaming kernel");
     printf("  search time with MMF_MMA_LEAN=1 (+ fast tail): %.3f ms (%.0f GB/s algorithmic)\n", ms_lean,
            rows_fp32 * 2048.0 / ms_lean * 1e-6);
+    }
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.3f ms (%.0f GB/s), streaming %.2f ms\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, ms_stream8);
     // batch-1 latency path (C3): exact streaming kernel vs its screened variant, 1 and 8 queries
-    for (int nqs = 1; nqs <= 8; nqs *= 8) {
+    for (int nqs = 1; nqs <= 8 && want("streamscreen"); nqs *= 8) {
       float ms_exact = 0, ms_scr = 0;
       unsetenv("MMF_STREAM_SCREEN");
       Result ex1 = search(nqs, k, MMF_ALGO_STREAM, &ms_exact, 20);
@@ -253,6 +276,7 @@ int main(int argc, char** argv) {
     Result screen2 = search(nq, k, MMF_ALGO_MMA);
     unsetenv("MMF_MMA_SCREEN");
     fails += !same(screen2, mma2, nq, k, "screened search, overflowing band vs 3-pass");
+    if (want("lean")) {
     setenv("MMF_MMA_SCREEN", "1", 1);
     setenv("MMF_MMA_LEAN", "1", 1);
     Result lean2 = search(nq, k, MMF_ALGO_MMA);
@@ -261,7 +285,8 @@ int main(int argc, char** argv) {
     unsetenv("MMF_MMA_SCREEN");
     fails += !same(lean2, mma2, nq, k, "lean sequence, overflowing band vs 3-pass");
     fails += !same(lean3, mma2, nq, k, "lean sequence, overflowing band, second call");
-    {
+    }
+    if (want("streamscreen")) {
       unsetenv("MMF_STREAM_SCREEN");
       Result ex2 = search(8, k, MMF_ALGO_STREAM);
       setenv("MMF_STREAM_SCREEN", "1", 1);
@@ -277,7 +302,7 @@ int main(int argc, char** argv) {
   }
 
   // ---------------- bf16 vault: bucket pool vs histogram bound (top-100, 4096 queries)
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 2 && want("bf16"); ++pass) {
     const int nq = 4096, k = 100;
     const long long rows_bf16 = pass == 0 ? rows_bf16_a : rows_bf16_b;
     if (rows_bf16 <= 0) continue;
@@ -307,7 +332,7 @@ int main(int argc, char** argv) {
            fl / ms_pool * 1e-9, ms_hist, fl / ms_hist * 1e-9);
   }
   // ---------------- sweep of small / ragged shapes (those of tests/test_gpu_parity.py), both variants, explicit switches
-  {
+  if (want("sweep")) {
     struct Shape { long long n; int nq, k; long long off; };
     const Shape shapes[] = {{1, 1, 1, 0}, {31, 3, 5, 0}, {128, 1, 1, 0}, {129, 130, 5, 0}, {150, 3, 12, 7}, {150, 3, 200, 0},
                             {1000, 1, 10, 0}, {2000, 40, 256, 0}, {3000, 64, 256, 100}, {4099, 2, 7, 0}, {5000, 16, 10, 0},
@@ -334,7 +359,7 @@ int main(int argc, char** argv) {
         setenv("MMF_MERGE_FAST", "1", 1);
         Result fast = search(sh.nq, sh.k, MMF_ALGO_MMA);
         setenv("MMF_MERGE_FAST", "0", 1);
-        if (mode == 0 && sh.k <= 16) {
+        if (mode == 0 && sh.k <= 16 && want("lean")) {
           setenv("MMF_MMA_LEAN", "1", 1);
           Result lean = search(sh.nq, sh.k, MMF_ALGO_MMA);
           unsetenv("MMF_MMA_LEAN");
@@ -345,7 +370,7 @@ int main(int argc, char** argv) {
         fails += !same(fast, var, sh.nq, sh.k, what_fast);
         if (mode == 0 && sh.k <= 16) {
           Result stream = search(sh.nq, sh.k, MMF_ALGO_STREAM);
-          if (sh.nq <= 64) {                         // the streaming kernel's own screened variant (small batches)
+          if (sh.nq <= 64 && want("streamscreen")) {   // the streaming kernel's own screened variant (small batches)
             setenv("MMF_STREAM_SCREEN", "1", 1);
             Result sscr = search(sh.nq, sh.k, MMF_ALGO_STREAM);
             unsetenv("MMF_STREAM_SCREEN");
@@ -363,7 +388,7 @@ int main(int argc, char** argv) {
     unsetenv("MMF_MERGE_FAST");
   }
   // ---------------- mmf_score_batch_host (one call, host buffers) vs the device entry points
-  {
+  if (want("host")) {
     printf("[score_batch_host] vs cosine + search + fusion through the device entry points\n");
     const int nq = 256, k = 10;
     const long long n = 300000;
@@ -452,7 +477,7 @@ int main(int argc, char** argv) {
   // B200_PROFILING.md: Xid 109), so both "ranks" use ONE stream and every exchange is enqueued as
   // push(rank 0), push(rank 1), merge(rank 0), merge(rank 1): when a merge kernel starts, all flags are already
   // set and nothing ever spins.  What this checks: slot layout, flags, epochs / parities, the merge itself.
-  {
+  if (want("exchange")) {
     printf("[exchange] 2 ranks' protocol, phases in sequence on one stream, vs the unsharded search\n");
     mmf_handle* R[2] = {nullptr, nullptr};
     cudaStream_t S;

@@ -10,9 +10,15 @@ run() {  # run <seconds> <log> <command...>
   timeout "$t" "$@" > "gpurun_out/$log" 2>&1
   echo "    rc=$?"
 }
-# 1. torch-free: every kernel variant against the others bit for bit, host entry, emulated 2-rank exchange, timings
-run 180 selftest.log tools/cabi_selftest 1000000 1250000 10000000
-grep -E "MISMATCH|selftest|search time|end to end" gpurun_out/selftest.log | tail -30
+# 1. torch-free: every kernel variant against the others bit for bit, with timings.  First the part that has already
+#    run green on a B200 (round 1), then each arm written without a GPU at hand in its OWN process, so that a fault
+#    in one cannot hide the others (SELFTEST_ONLY / SELFTEST_SKIP: see tools/cabi_selftest.cu).
+SELFTEST_SKIP=deep,prefetch,lean,streamscreen,host,exchange run 180 selftest_core.log tools/cabi_selftest 1000000 1250000 10000000
+grep -E "MISMATCH|selftest|search time" gpurun_out/selftest_core.log | tail -12
+for arm in deep prefetch lean streamscreen host exchange; do
+  SELFTEST_ONLY=$arm run 120 "selftest_$arm.log" tools/cabi_selftest
+  grep -E "MISMATCH|selftest|search time|batch-|end to end|CUDA error|mmf error" "gpurun_out/selftest_$arm.log" | tail -8
+done
 # 2. does 1 KB of every 2 KB cost HBM efficiency?
 run 60 hbm_stride.log tools/hbm_stride_micro
 cat gpurun_out/hbm_stride.log
