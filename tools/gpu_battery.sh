@@ -16,7 +16,9 @@ run() {  # run <seconds> <log> <command...>
 SELFTEST_SKIP=deep,prefetch,lean,streamscreen,host,exchange run 180 selftest_core.log tools/cabi_selftest 1000000 1250000 10000000
 grep -E "MISMATCH|selftest|search time" gpurun_out/selftest_core.log | tail -12
 for arm in deep prefetch lean streamscreen host exchange; do
-  SELFTEST_ONLY=$arm run 120 "selftest_$arm.log" tools/cabi_selftest
+  only=$arm
+  case $arm in lean|streamscreen) only="$arm,sweep";; esac      # these two also have arms in the shape sweep
+  SELFTEST_ONLY=$only run 120 "selftest_$arm.log" tools/cabi_selftest
   grep -E "MISMATCH|selftest|search time|batch-|end to end|CUDA error|mmf error" "gpurun_out/selftest_$arm.log" | tail -8
 done
 # 2. does 1 KB of every 2 KB cost HBM efficiency?
