@@ -1,0 +1,73 @@
+"""TEST DOUBLE -- an Engine look-alike whose arithmetic is the CPU oracle.
+
+It exists so that the HOST logic of the drop-in layer (mmf_b200.forensics / clip_similarity_engine / pipeline /
+vault: argument handling, modality rules, match records, video aggregation, return schemas, error behaviour) can
+be exercised against the reference fixtures in the CPU test-suite.  It lives in tests/ and is never imported by the
+package; the product Engine has no CPU path (tests/test_host_cpu.py::test_no_cpu_fallback)."""
+import numpy as np
+import torch
+
+import oracle
+
+
+class OracleEngine:
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.launch_count = 0
+        self._vault = None
+        self._row_offset = 0
+        self._weights = None
+        self.vault_rows = 0
+        self.vault_mode = None
+
+    @staticmethod
+    def _np(x, cols):
+        t = torch.as_tensor(x).detach().to("cpu", torch.float32)
+        return np.ascontiguousarray(t.reshape(-1, cols).numpy())
+
+    def cosine_pairs(self, a, b, match_threshold=None):
+        dim = torch.as_tensor(a).shape[-1]
+        sim = torch.from_numpy(np.asarray(oracle.cosine_pairs(self._np(a, dim), self._np(b, dim)), np.float32))
+        if match_threshold is None:
+            return sim
+        return sim, torch.from_numpy((sim.numpy().astype(np.float64) >= float(match_threshold)).astype(np.uint8))
+
+    def vault_load(self, rows, mode="fp32", row_offset=0):
+        arr = rows.detach().cpu().numpy() if isinstance(rows, torch.Tensor) else np.asarray(rows)
+        if arr.ndim != 2 or arr.shape[1] != 512:
+            raise ValueError("vault rows must be (n, 512)")
+        self._vault = oracle.vault_normalise(arr.astype(np.float32)).astype(np.float32)   # the library normalises in fp32
+        self._row_offset, self.vault_rows, self.vault_mode = int(row_offset), arr.shape[0], mode
+
+    def vault_unload(self):
+        self._vault, self.vault_rows, self.vault_mode = None, 0, None
+
+    def vault_search(self, queries, top_k=5, threshold=oracle.VAULT_THRESHOLD, algo="auto"):
+        q = self._np(queries, 512)
+        idx, sc, _ = oracle.vault_search_batched(self._vault, q, top_k, vault_is_normalised=True, row_offset=self._row_offset)
+        nq, kk = idx.shape
+        rows = np.full((nq, top_k), -1, np.int64)
+        scores = np.full((nq, top_k), np.nan, np.float32)
+        rows[:, :kk], scores[:, :kk] = idx, sc
+        disc = oracle.discrepancy_rule(sc[:, 0], threshold) if kk else np.zeros(nq, np.float32)
+        return torch.from_numpy(scores), torch.from_numpy(rows), torch.from_numpy(disc)
+
+    def fusion_load(self, state_dict):
+        pre = "" if "0.weight" in state_dict else "fusion_layer."
+        self._weights = {k: torch.as_tensor(state_dict[pre + k]).detach().float().cpu() for k in oracle.FUSION_KEYS}
+
+    def fusion_forward(self, x):
+        p = np.asarray(oracle.fusion_forward(self._weights, self._np(x, 5)), np.float32)
+        verdict = (p[:, 1] > 0.5).astype(np.int32)
+        conf = np.where(verdict == 1, p[:, 1], p[:, 0]).astype(np.float32)
+        return torch.from_numpy(p), torch.from_numpy(verdict), torch.from_numpy(conf)
+
+    def verdict_batch(self, scores, modality):
+        x = self._np(scores, 5)
+        mod = torch.as_tensor(modality).to(torch.uint8).numpy()
+        p, verdict, conf = (t.numpy().copy() for t in self.fusion_forward(x))
+        for i in np.nonzero(mod != 3)[0]:
+            d = oracle.fallback_verdict(dict(zip(oracle.FUSION_ORDER, map(float, x[i]))), bool(mod[i] & 1), bool(mod[i] & 2))
+            p[i] = (d["real_probability"], d["fake_probability"])
+            verdict[i], conf[i] = d["verdict"], d["confidence"]
+        return torch.from_numpy(p), torch.from_numpy(verdict), torch.from_numpy(conf)

@@ -1,0 +1,130 @@
+"""Host logic of the drop-in layer on the CPU: mmf_b200.MisinfoForensics / CLIPSimilarityEngine driven through the
+OracleEngine test double (tests/cpu_engine.py) must reproduce the fixtures that the REFERENCE'S OWN methods produced
+(tests/golden, SURVEY.md 8b: same signatures, return schemas, error behaviour).  The arithmetic here is the oracle's;
+the CUDA arithmetic is checked by the `-m gpu` suite with the same fixtures and the same comparison helpers."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import fakes
+from conftest import GOLDEN
+from cpu_engine import OracleEngine
+from test_gpu_parity import _cmp_result, _load_analyze_fixture
+from util import FP32_TOL
+
+import mmf_b200
+
+
+def _forensics(g, cases, **kw):
+    det = fakes.FakeDetector(g["ai"], g["misinfo"], g["deepfake"], fusion_seed=5)
+    return mmf_b200.MisinfoForensics(
+        detector=det, roberta_tokenizer=fakes.FakeTokenizer(), clip_model=fakes.FakeClipModel(g["image_table"], g["text_table"]),
+        clip_processor=fakes.FakeClipProcessor(), vault={"embeddings": g["vault"], "metadata": cases["metadata"]},
+        engine=OracleEngine(), **kw)
+
+
+def test_analyze_host_logic_matches_reference(capsys):
+    g, cases = _load_analyze_fixture()
+    f = _forensics(g, cases)
+    assert f.vault_loaded and len(f.vault_metadata) == len(cases["metadata"])
+    for c in cases["cases"]:
+        i = c["id"]
+        text = fakes.text_for_id(i) if c["mode"] in ("both", "text") else None
+        image = fakes.image_for_id(i) if c["mode"] in ("both", "image") else None
+        _cmp_result(f.analyze(text=text, image_path=image, verbose=(i % 7 == 0)), c["result"], f"case {i} ({c['mode']})")
+    assert capsys.readouterr().out                                        # verbose=True prints the per-step scores
+    with pytest.raises(ValueError, match="Provide at least one of"):
+        f.analyze(verbose=False)
+    sv = f.search_vault(fakes.image_for_id(0), user_caption=fakes.text_for_id(0), top_k=3)
+    assert set(sv) == {"vault_discrepancy", "matches", "vault_available", "text_similarity"} and len(sv["matches"]) == 3
+    assert set(sv["matches"][0]) == {"similarity", "title", "url", "date"}
+    assert set(f.fusion_verdict({"ai_score": 0.3})) == {"verdict", "confidence", "fake_probability", "real_probability"}
+    assert set(f.analyze_consistency(fakes.text_for_id(1), fakes.image_for_id(1))) == {"clip_similarity"}
+
+
+def test_analyze_batch_score_matrix_and_dedup_host_logic():
+    g, cases = _load_analyze_fixture()
+    f = _forensics(g, cases)
+    texts = [fakes.text_for_id(c["id"]) if c["mode"] in ("both", "text") else None for c in cases["cases"]]
+    images = [fakes.image_for_id(c["id"]) if c["mode"] in ("both", "image") else None for c in cases["cases"]]
+    for got, c in zip(f.analyze_batch(texts, images), cases["cases"]):
+        _cmp_result(got, c["result"], f"batch case {c['id']} ({c['mode']})")
+    assert f.score_matrix(texts, images).shape == (len(texts), 5)
+    f2 = _forensics(g, cases, dedup_clip_encode=False)
+    for c in cases["cases"][:6]:
+        assert f.analyze(text=texts[c["id"]], image_path=images[c["id"]], verbose=False) == \
+               f2.analyze(text=texts[c["id"]], image_path=images[c["id"]], verbose=False)
+    with pytest.raises(ValueError):
+        f.analyze_batch([None], [None])
+
+
+def test_video_aggregation_host_logic(monkeypatch):
+    g, cases = _load_analyze_fixture()
+    f = _forensics(g, cases)
+    monkeypatch.setitem(sys.modules, "cv2", fakes.FakeCv2)
+    for v in cases["videos"]:
+        got = f.analyze_video(v["path"], text=v["text"], max_frames=12, stride_seconds=1.0)
+        got.pop("best_frame")
+        for key in ("deepfake_score", "clip_similarity", "vault_discrepancy", "text_similarity"):
+            assert abs(got[key] - v["video"][key]) <= FP32_TOL, (v["path"], key)
+        assert [m["title"] for m in got["vault_matches"]] == [m["title"] for m in v["video"]["vault_matches"]]
+        _cmp_result(f.analyze(text=v["text"], video_path=v["path"], verbose=False), v["result"], v["path"])
+    with pytest.raises(RuntimeError, match="Could not open video"):
+        f.analyze_video("nope.mp4")
+
+
+def test_vault_missing_and_builder_pickle_host_logic(tmp_path):
+    import pickle
+    g, cases = _load_analyze_fixture()
+    det = fakes.FakeDetector(g["ai"], g["misinfo"], g["deepfake"], fusion_seed=5)
+    common = dict(detector=det, roberta_tokenizer=fakes.FakeTokenizer(), clip_processor=fakes.FakeClipProcessor(),
+                  clip_model=fakes.FakeClipModel(g["image_table"], g["text_table"]))
+    f = mmf_b200.MisinfoForensics(faiss_index_path=str(tmp_path / "missing.pkl"), engine=OracleEngine(), **common)
+    assert f.vault_loaded is False
+    assert f.search_vault(fakes.image_for_id(0)) == {"vault_discrepancy": 0.0, "matches": [], "vault_available": False,
+                                                    "text_similarity": 0.0}
+    r = f.analyze(text=fakes.text_for_id(1), image_path=fakes.image_for_id(1), verbose=False)
+    assert r["scores"]["vault_discrepancy"] == 0.0 and r["vault_matches"] == []
+    n = 300
+    p = tmp_path / "guardian_embeddings.pkl"
+    with open(p, "wb") as fh:
+        pickle.dump({"article_ids": [str(i) for i in range(n)], "text_contents": [fakes.text_for_id(i) for i in range(n)],
+                     "image_paths": [f"img/{i}.jpg" for i in range(n)], "image_embeddings": g["vault"][:n].astype(np.float16),
+                     "text_embeddings": g["vault"][:n].astype(np.float16), "metadata": {"total_articles": n}}, fh)
+    f2 = mmf_b200.MisinfoForensics(faiss_index_path=str(p), engine=OracleEngine(), **common)
+    assert f2.vault_loaded and len(f2.vault_metadata) == n and f2.vault_embeddings.dtype == np.float16
+    sv = f2.search_vault(fakes.image_for_id(0))
+    assert sv["vault_available"] and sv["matches"][0]["date"] == "N/A" and sv["matches"][0]["url"].startswith("img/")
+
+
+def test_clip_similarity_engine_host_logic(tmp_path):
+    g = np.load(os.path.join(GOLDEN, "cosine.npz"))
+    e = mmf_b200.CLIPSimilarityEngine(model=fakes.FakeClipModel(g["image"], g["text"]), processor=fakes.FakeClipProcessor(),
+                                      threshold=0.25, engine=OracleEngine())
+    paths = []
+    for i in range(12):
+        p = tmp_path / f"{i}.png"
+        fakes.image_for_id(i).save(p)
+        paths.append(str(p))
+    for i, p in enumerate(paths):
+        sim, label = e.calculate_similarity(p, fakes.text_for_id(i))
+        assert abs(sim - g["engine_similarity"][i]) <= FP32_TOL
+        if abs(g["engine_similarity"][i] - 0.25) > FP32_TOL:
+            assert (label == "Match") == bool(g["engine_match"][i])
+        out = e.analyze_with_explanation(p, fakes.text_for_id(i))
+        assert out["label"] == label and out["similarity_score"] == round(sim, 4)
+        assert out["explanation"].split("(")[0] == str(g["engine_explanation"][i]).split("(")[0]
+    with pytest.raises(FileNotFoundError):
+        e.calculate_similarity(str(tmp_path / "missing.png"), "caption #1")
+    with pytest.raises(ValueError):
+        e.calculate_similarity(paths[0], "")
+    bad = tmp_path / "bad.png"
+    bad.write_bytes(b"not an image")
+    with pytest.raises(ValueError):
+        e.calculate_similarity(str(bad), "caption #1")
+    assert "error" in e.analyze_with_explanation(str(bad), "caption #1")
+    json.dumps(e.analyze_with_explanation(paths[0], fakes.text_for_id(0)))
