@@ -128,3 +128,27 @@ def test_clip_similarity_engine_host_logic(tmp_path):
         e.calculate_similarity(str(bad), "caption #1")
     assert "error" in e.analyze_with_explanation(str(bad), "caption #1")
     json.dumps(e.analyze_with_explanation(paths[0], fakes.text_for_id(0)))
+
+
+def test_score_batch_host_logic_equals_scalar_fixtures():
+    """pipeline.score_batch (modality masks, score assembly, verdict rule) per row == the reference's scalar analyze"""
+    g, cases = _load_analyze_fixture()
+    f = _forensics(g, cases)
+    ns = len(g["ai"])
+    head = np.zeros((ns, 3), np.float32)
+    for c in cases["cases"]:
+        sc = c["result"]["scores"]
+        head[c["id"]] = [sc["ai_score"], sc["misinfo_score"], sc["deepfake_score"]]
+    mod = np.array([3 if c["mode"] == "both" else 1 if c["mode"] == "text" else 2 for c in cases["cases"]], np.uint8)
+    out = f.score_batch(g["text_table"][:ns], g["image_table"][:ns], head, mod, top_k=5)
+    assert set(out) == {"clip_similarity", "vault_discrepancy", "vault_scores", "vault_rows", "scores", "probs", "verdict", "confidence"}
+    for c in cases["cases"]:
+        i, want = c["id"], c["result"]["scores"]
+        assert abs(out["clip_similarity"][i].item() - want["clip_similarity"]) <= FP32_TOL
+        assert abs(out["vault_discrepancy"][i].item() - want["vault_discrepancy"]) <= FP32_TOL
+        assert abs(out["probs"][i, 1].item() - want["fake_probability"]) <= FP32_TOL
+        if abs(want["fake_probability"] - 0.5) > FP32_TOL:
+            assert out["verdict"][i].item() == want["verdict"]
+    # no modality mask = both present; no vault = zero discrepancy, no rows
+    out2 = mmf_b200.score_batch(f.engine, None, g["text_table"][:4], g["image_table"][:4], head[:4], None, 5)
+    assert torch.all(out2["vault_rows"] == -1) and torch.all(out2["vault_discrepancy"] == 0)
