@@ -71,3 +71,24 @@ class OracleEngine:
             p[i] = (d["real_probability"], d["fake_probability"])
             verdict[i], conf[i] = d["verdict"], d["confidence"]
         return torch.from_numpy(p), torch.from_numpy(verdict), torch.from_numpy(conf)
+
+    # ---- row-sharded search: packed candidates + merge (csrc/topk.cuh: key = order-preserving score << 32 | row)
+    def vault_search_candidates(self, queries, top_k, algo="auto"):
+        q = self._np(queries, 512)
+        idx, sc, _ = oracle.vault_search_batched(self._vault, q, top_k, vault_is_normalised=True, row_offset=self._row_offset)
+        packed = np.zeros((q.shape[0], top_k), np.uint64)                 # 0 = empty slot
+        packed[:, :idx.shape[1]] = oracle.order_key64(sc, idx)
+        return torch.from_numpy(packed.view(np.int64))
+
+    def topk_merge(self, packed, top_k, threshold=oracle.VAULT_THRESHOLD):
+        keys = np.ascontiguousarray(packed.cpu().numpy()).view(np.uint64)              # (n_lists, Q, k_in)
+        n_lists, nq, k_in = keys.shape
+        flat = np.sort(keys.transpose(1, 0, 2).reshape(nq, n_lists * k_in), axis=1)[:, ::-1][:, :top_k]
+        if flat.shape[1] < top_k:
+            flat = np.concatenate([flat, np.zeros((nq, top_k - flat.shape[1]), np.uint64)], axis=1)
+        u = (flat >> np.uint64(32)).astype(np.uint32)
+        bits = np.where(u & np.uint32(0x80000000), u & np.uint32(0x7FFFFFFF), ~u).astype(np.uint32)
+        scores = np.where(flat != 0, bits.view(np.float32), np.float32(np.nan)).astype(np.float32)
+        rows = np.where(flat != 0, (flat & np.uint64(0xFFFFFFFF)).astype(np.int64), -1)
+        disc = np.where(flat[:, 0] != 0, oracle.discrepancy_rule(np.nan_to_num(scores[:, 0], nan=0.0), threshold), 0).astype(np.float32)
+        return torch.from_numpy(scores), torch.from_numpy(rows), torch.from_numpy(disc)

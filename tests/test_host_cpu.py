@@ -255,3 +255,58 @@ def test_screened_search_argument_holds_on_emulated_operands():
             assert set(want) <= set(band), (name, i)
             got = band[np.argsort(exact[i][band], kind="stable")[-k:]]
             assert np.array_equal(np.sort(exact[i][got]), np.sort(exact[i][want])), (name, i)
+
+
+def _sharded_vault_worker(rank, world, port, out):
+    import torch.distributed as dist
+    sys_path = os.path.join(ROOT, "tests")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    from cpu_engine import OracleEngine
+    from mmf_b200 import synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_rows, k = 1203, 10
+        vault = synth.vault_rows(n_rows, seed=5)
+        vault[900] = vault[3]                                    # a tie across the shard boundary
+        q, _, _ = synth.queries(7, n_rows, seed=6, plant_frac=0.5, vault_seed=5)
+        q[0] = vault[3]
+        # TruthVault slices the full array itself (rank / world) ...
+        tv = mmf_b200.TruthVault(OracleEngine(), vault, None, mode="fp32", rank=rank, world=world)
+        s1, r1, d1 = tv.search(torch.from_numpy(q), k)
+        # ... or takes this rank's shard of an n_total-row vault
+        lo, hi = mmf_b200.ShardPlan(n_rows, world).bounds(rank)
+        tv2 = mmf_b200.TruthVault(OracleEngine(), vault[lo:hi], None, mode="fp32", rank=rank, world=world, n_total=n_rows, row_offset=lo)
+        s2, r2, d2 = tv2.search(torch.from_numpy(q), k)
+        fi, fs, fd = oracle.vault_search_batched(vault, q, k)
+        for s, r, d in ((s1, r1, d1), (s2, r2, d2)):
+            assert np.array_equal(r.numpy(), fi) and np.allclose(s.numpy(), fs, atol=2e-6) and np.allclose(d.numpy(), fd, atol=2e-6)
+        assert list(r1.numpy()[0, :2]) == [900, 3]
+        # top_k larger than a shard: every rank contributes all of its rows
+        s3, r3, _ = mmf_b200.TruthVault(OracleEngine(), vault[:9], None, rank=rank, world=world).search(torch.from_numpy(q), 8)
+        gi, gs, _ = oracle.vault_search_batched(vault[:9], q, 8)
+        assert np.array_equal(r3.numpy(), gi)
+        out.put((rank, True, ""))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        out.put((rank, False, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_truth_vault_search_over_gloo_world2():
+    """TruthVault.search with world = 2 end to end on the CPU (shard planning, k_local, the all-gather, the merge order);
+    the per-shard arithmetic is the oracle's (tests/cpu_engine.py), the collective runs over gloo"""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_vault_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [out.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok, _ in res), res
