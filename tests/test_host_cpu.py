@@ -310,3 +310,31 @@ def test_sharded_truth_vault_search_over_gloo_world2():
     for p in procs:
         p.join(60)
     assert all(ok for _, ok, _ in res), res
+
+
+def test_every_entry_point_rejects_a_null_handle():
+    """error convention of the C ABI: int status, no crash, no C++ exception -- checked without a GPU
+    by handing every handle-taking entry point a NULL handle"""
+    lib = _lib.load()
+    N = None
+    bad_arg = {
+        "mmf_cosine_pairs": (N, N, N, 0, 512, 0.0, N, N, N),
+        "mmf_vault_load": (N, N, 0, 0, 512, 0, 0, 0), "mmf_vault_unload": (N,), "mmf_vault_info": (N, N, N, N, N),
+        "mmf_vault_search": (N, N, 0, 5, 0.85, 0, N, N, N, N), "mmf_vault_search_host": (N, N, 0, 5, 0.85, 0, N, N, N),
+        "mmf_vault_search_candidates": (N, N, 0, 5, 0, N, N), "mmf_topk_merge": (N, N, 1, 0, 5, 5, 0.85, N, N, N, N),
+        "mmf_fusion_load": (N, N), "mmf_fusion_forward": (N, N, 0, N, N, N, N), "mmf_verdict_batch": (N, N, N, 0, N, N, N, N),
+        "mmf_score_batch_host": (N, N, N, N, N, 0, 5, 0.85, 0, N, N, N, N, N, N, N, N),
+        "mmf_exchange_attach": (N, 0, 1, N, 0), "mmf_vault_search_push": (N, N, 0, 5, 0, N),
+        "mmf_vault_exchange_merge": (N, 5, 0.85, N, N, N, N), "mmf_vault_search_exchange": (N, N, 0, 5, 5, 0.85, 0, N, N, N, N),
+    }
+    for name, args in bad_arg.items():
+        assert getattr(lib, name)(*args) == _lib.ERR_BAD_ARG, name
+    assert lib.mmf_destroy(None) == 0 and lib.mmf_exchange_detach(None) == 0 and lib.mmf_launch_count(None) == 0
+    assert lib.mmf_last_error(None) == b"null handle"
+    handle_free = {"mmf_version", "mmf_arch", "mmf_status_string", "mmf_create", "mmf_mma_plan_check", "mmf_mma_hist_bound",
+                   "mmf_mma_screen_eps", "mmf_exchange_layout", "mmf_destroy", "mmf_exchange_detach", "mmf_launch_count",
+                   "mmf_last_error"}
+    assert set(bad_arg) | handle_free == set(_lib.SIGNATURES)            # nothing left unchecked
+    for code, text in ((0, b"ok"), (-1, b"bad argument"), (-2, b"CUDA error"), (-4, b"no CUDA device"), (-5, b"unsupported"),
+                       (-6, b"out of device memory"), (-99, b"unknown status")):
+        assert lib.mmf_status_string(code) == text
