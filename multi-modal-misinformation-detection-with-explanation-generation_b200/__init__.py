@@ -12,3 +12,4 @@ from .vault import ShardPlan, TruthVault, exchange_candidates, load_vault_file, 
 from .pipeline import score_batch  # noqa: F401
 from .forensics import MisinfoForensics, MultiModalMisinfoDetector  # noqa: F401
 from .clip_similarity_engine import CLIPSimilarityEngine  # noqa: F401
+from .similar_articles import search_similar_articles  # noqa: F401

@@ -19,7 +19,7 @@ __all__ = [
     "vault_search_as_shipped", "vault_normalise", "vault_search_batched", "order_key64",
     "discrepancy_rule", "merge_topk", "fusion_weights_from_checkpoint", "fusion_forward",
     "fusion_verdict", "fallback_verdict", "assemble_verdict", "video_aggregate",
-    "read_vault_dict",
+    "read_vault_dict", "similar_articles_as_shipped",
 ]
 
 VAULT_THRESHOLD = 0.85   # misinfo_forensics.py:464,468
@@ -180,6 +180,17 @@ def read_vault_dict(vault_data: dict):
                  "date": "N/A"} for i in range(len(texts))]
         return vault_data["image_embeddings"], meta
     return None, None
+
+
+def similar_articles_as_shipped(db_embeddings: np.ndarray, query_embed: np.ndarray, top_k: int = 5):
+    """Numeric core of search_similar_articles, train_clip_detective.py:657-664: the query is normalised with NumPy,
+    the database rows are used AS STORED (the writer normalised them, :556-557 -- no renormalisation here, unlike
+    search_vault), full descending argsort, first k.  Returns (indices int64 (k,), similarities (k,))."""
+    q = np.asarray(query_embed)
+    q = q / np.linalg.norm(q)                                               # :657
+    sims = np.dot(db_embeddings, q)                                         # :660
+    idx = np.argsort(sims)[::-1][:top_k]                                    # :663
+    return idx.astype(np.int64), sims[idx]
 
 
 # --------------------------------------------------------------------------- fusion judge

@@ -226,7 +226,78 @@ def gen_analyze():
     print("analyze_cases.json", len(cases), "cases,", nf, "FAKE;", len(vids), "videos")
 
 
+def gen_similar():
+    """search_similar_articles (train_clip_detective.py:610-688), SURVEY.md 8f rank 4: the REFERENCE'S OWN function is
+    run; only what it loads from disk / the network is swapped -- CLIPProcessor / CLIPDetective / the checkpoint become
+    the fakes (rows of seeded tables), `optuna` (imported at module level, not installed here, never used on this
+    path) becomes an empty module.  The similarity arithmetic (:657-664) runs unmodified."""
+    import pickle
+    import tempfile
+    import types
+    if "optuna" not in sys.modules:
+        opt = types.ModuleType("optuna")
+        opt.trial = types.ModuleType("optuna.trial")
+        opt.trial.TrialState = object
+        sys.modules["optuna"], sys.modules["optuna.trial"] = opt, opt.trial
+    with contextlib.redirect_stdout(io.StringIO()):
+        import train_clip_detective as ref_tc
+    n, nq, k = 800, 12, 5
+    g = np.random.default_rng(70)
+    img_db = synth.vault_rows(n, seed=71)                  # the writer L2-normalises the rows (:556-557)
+    txt_db = synth.vault_rows(n, seed=72)
+    img_db /= np.linalg.norm(img_db, axis=1, keepdims=True)
+    txt_db /= np.linalg.norm(txt_db, axis=1, keepdims=True)
+    txt_q = g.standard_normal((nq, 512)).astype(np.float32) * 3
+    img_q = g.standard_normal((nq, 512)).astype(np.float32) * 0.5
+    for i in range(0, nq, 2):                              # half of the queries are near a database row
+        txt_q[i] = synth.planted_query(txt_db[37 * i + 5], 0.9, g) * 2
+        img_q[i] = synth.planted_query(img_db[41 * i + 3], 0.95, g) * 7
+    txt_q[1] = txt_db[700]                                 # exact hit
+    db = {"article_ids": [f"art-{i}" for i in range(n)], "text_contents": [("headline %d " % i) * 30 for i in range(n)],
+          "image_paths": [f"images/{i}.jpg" for i in range(n)], "image_embeddings": img_db, "text_embeddings": txt_db,
+          "metadata": {"total_articles": n, "embedding_dim": 512}}
+
+    class FakeDetective(torch.nn.Module):
+        def __init__(self, *a, **kw):
+            super().__init__()
+            self.clip = fakes.FakeClipModel(img_q, txt_q)
+
+        def load_state_dict(self, *a, **kw):
+            return None
+
+    out = {"text": [], "image": [], "text_f16": []}
+    with tempfile.TemporaryDirectory() as tmp:
+        for i in range(nq):
+            fakes.image_for_id(i).save(os.path.join(tmp, f"q{i}.png"))
+        real = (ref_tc.CLIPProcessor, ref_tc.CLIPDetective, torch.load)
+        ref_tc.CLIPProcessor = types.SimpleNamespace(from_pretrained=lambda *a, **kw: fakes.FakeClipProcessor())
+        ref_tc.CLIPDetective = FakeDetective
+        torch.load = lambda *a, **kw: {"model_state_dict": {}}
+        try:
+            for tag, d in (("f32", db), ("f16", dict(db, text_embeddings=txt_db.astype(np.float16)))):
+                path = os.path.join(tmp, f"db_{tag}.pkl")
+                with open(path, "wb") as fh:
+                    pickle.dump(d, fh)
+                for i in range(nq):
+                    r = quiet(ref_tc.search_similar_articles, query_text=fakes.text_for_id(i), embeddings_db_path=path,
+                              top_k=k, search_mode="text")
+                    out["text" if tag == "f32" else "text_f16"].append(r)
+                    if tag == "f32":
+                        out["image"].append(quiet(ref_tc.search_similar_articles, query_image_path=os.path.join(tmp, f"q{i}.png"),
+                                                  embeddings_db_path=path, top_k=k, search_mode="image"))
+        finally:
+            ref_tc.CLIPProcessor, ref_tc.CLIPDetective, torch.load = real
+    np.savez_compressed(os.path.join(HERE, "similar.npz"), image_embeddings=img_db, text_embeddings=txt_db, text_queries=txt_q,
+                        image_queries=img_q)
+    with open(os.path.join(HERE, "similar_cases.json"), "w") as fh:
+        json.dump({"top_k": k, "article_ids": db["article_ids"], "text_contents": db["text_contents"],
+                   "image_paths": db["image_paths"], "results": out}, fh)
+    print("similar_cases.json", nq, "queries x 3 modes; top hit of query 1:", out["text"][1][0]["article_id"],
+          out["text"][1][0]["similarity"])
+
+
 if __name__ == "__main__":
+    gen_similar()
     gen_cosine()
     gen_vault()
     gen_fusion()

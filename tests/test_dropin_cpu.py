@@ -152,3 +152,43 @@ def test_score_batch_host_logic_equals_scalar_fixtures():
     # no modality mask = both present; no vault = zero discrepancy, no rows
     out2 = mmf_b200.score_batch(f.engine, None, g["text_table"][:4], g["image_table"][:4], head[:4], None, 5)
     assert torch.all(out2["vault_rows"] == -1) and torch.all(out2["vault_discrepancy"] == 0)
+
+
+def test_search_similar_articles_host_logic(tmp_path, capsys):
+    """drop-in for train_clip_detective.search_similar_articles: records (rank, article_id, similarity, text, image_path)
+    equal the reference's; fp16 databases inside the documented 1e-2 band (we renormalise the rows in fp32)"""
+    g = np.load(os.path.join(GOLDEN, "similar.npz"))
+    with open(os.path.join(GOLDEN, "similar_cases.json")) as fh:
+        c = json.load(fh)
+    k = c["top_k"]
+    db = {"article_ids": c["article_ids"], "text_contents": c["text_contents"], "image_paths": c["image_paths"],
+          "image_embeddings": g["image_embeddings"], "text_embeddings": g["text_embeddings"]}
+    clip = fakes.FakeClipModel(g["image_queries"], g["text_queries"])
+    common = dict(clip_model=clip, processor=fakes.FakeClipProcessor(), engine=OracleEngine())
+    for i, want in enumerate(c["results"]["text"]):
+        got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(i), top_k=k, search_mode="text", embeddings_db=db, **common)
+        assert [(r["rank"], r["article_id"], r["text"], r["image_path"]) for r in got] == \
+               [(r["rank"], r["article_id"], r["text"], r["image_path"]) for r in want], i
+        assert np.allclose([r["similarity"] for r in got], [r["similarity"] for r in want], atol=FP32_TOL)
+    for i, want in enumerate(c["results"]["image"]):
+        p = tmp_path / f"q{i}.png"
+        fakes.image_for_id(i).save(p)
+        got = mmf_b200.search_similar_articles(query_image_path=str(p), top_k=k, search_mode="image", embeddings_db=db, **common)
+        assert [r["article_id"] for r in got] == [r["article_id"] for r in want], i
+        assert np.allclose([r["similarity"] for r in got], [r["similarity"] for r in want], atol=FP32_TOL)
+    db16 = dict(db, text_embeddings=g["text_embeddings"].astype(np.float16))
+    for i, want in enumerate(c["results"]["text_f16"][:4]):
+        got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(i), top_k=k, embeddings_db=db16, **common)
+        assert got[0]["article_id"] == want[0]["article_id"]
+        assert np.allclose([r["similarity"] for r in got], [r["similarity"] for r in want], atol=1e-2)
+    # the pickle path, top_k larger than the database, and the reference's error
+    import pickle
+    small = {key: (v[:3] if not isinstance(v, dict) else v) for key, v in db.items()}
+    with open(tmp_path / "db.pkl", "wb") as fh:
+        pickle.dump(small, fh)
+    got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(1), embeddings_db_path=str(tmp_path / "db.pkl"), top_k=5, **common)
+    assert len(got) == 3 and [r["rank"] for r in got] == [1, 2, 3]
+    with pytest.raises(ValueError, match="Invalid search mode or missing query"):
+        mmf_b200.search_similar_articles(search_mode="text", embeddings_db=db, **common)
+    assert "Top 5 similar articles" in capsys.readouterr().out
+    json.dumps(got)

@@ -280,3 +280,29 @@ def test_screened_search_experiments_change_nothing(eng, switches):
             again = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
         for a, b, c in zip(got, want, again):
             assert np.array_equal(a, b, equal_nan=True) and np.array_equal(c, b, equal_nan=True), (switches, n_rows)
+
+
+def test_search_similar_articles_dropin_on_gpu(tmp_path):
+    """8f rank 4: search_similar_articles through the real kernels vs the fixtures of the reference's own function"""
+    import json
+    import fakes
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "similar.npz"))
+    with open(os.path.join(GOLDEN, "similar_cases.json")) as fh:
+        c = json.load(fh)
+    k = c["top_k"]
+    db = {"article_ids": c["article_ids"], "text_contents": c["text_contents"], "image_paths": c["image_paths"],
+          "image_embeddings": g["image_embeddings"], "text_embeddings": g["text_embeddings"]}
+    engine = mmf_b200.Engine("cuda:0")
+    common = dict(clip_model=fakes.FakeClipModel(g["image_queries"], g["text_queries"]), processor=fakes.FakeClipProcessor(), engine=engine)
+    for i, want in enumerate(c["results"]["text"]):
+        got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(i), top_k=k, embeddings_db=db, **common)
+        assert [r["article_id"] for r in got] == [r["article_id"] for r in want], i
+        assert np.allclose([r["similarity"] for r in got], [r["similarity"] for r in want], atol=FP32_TOL)
+    for i, want in enumerate(c["results"]["image"]):
+        p = tmp_path / f"q{i}.png"
+        fakes.image_for_id(i).save(p)
+        got = mmf_b200.search_similar_articles(query_image_path=str(p), top_k=k, search_mode="image", embeddings_db=db, **common)
+        assert [r["article_id"] for r in got] == [r["article_id"] for r in want], i
+        assert np.allclose([r["similarity"] for r in got], [r["similarity"] for r in want], atol=FP32_TOL)
+    engine.close()

@@ -132,3 +132,21 @@ def test_analyze_assembly_matches_reference():
         assert close(v["fake_probability"], sc["fake_probability"], 1e-6)
     for v in cases["videos"]:
         assert v["result"]["scores"]["vault_discrepancy"] == v["video"]["vault_discrepancy"]
+
+
+def test_similar_articles_matches_reference():
+    """search_similar_articles (train_clip_detective.py:610-688): fixtures produced by the
+    reference's own function (tests/golden/make_golden.py: gen_similar)"""
+    import json
+    g = np.load(os.path.join(GOLDEN, "similar.npz"))
+    with open(os.path.join(GOLDEN, "similar_cases.json")) as fh:
+        c = json.load(fh)
+    k = c["top_k"]
+    for mode, db, queries in (("text", g["text_embeddings"], g["text_queries"]), ("image", g["image_embeddings"], g["image_queries"]),
+                              ("text_f16", g["text_embeddings"].astype(np.float16), g["text_queries"])):
+        for i, want in enumerate(c["results"][mode]):
+            idx, sims = oracle.similar_articles_as_shipped(db, queries[i], k)
+            assert [c["article_ids"][j] for j in idx] == [r["article_id"] for r in want], (mode, i)
+            assert np.allclose(sims, [r["similarity"] for r in want], atol=5e-7 if mode != "text_f16" else 2e-3), (mode, i)
+            assert [r["rank"] for r in want] == list(range(1, k + 1))
+            assert want[0]["text"] == c["text_contents"][idx[0]][:100] + "..." and want[0]["image_path"] == c["image_paths"][idx[0]]
