@@ -107,3 +107,85 @@ def read_metadata(path: str, rows: Optional[Iterable[int]] = None) -> List[dict]
             elif i in want:
                 out[i] = json.loads(line)
     return out if want is None else [out[int(r)] for r in rows]
+
+
+def generate_embeddings_database(model_path: str = "clip_detective_best.pth", json_file: str = "vector_db_seed.json",
+                                 output_file: str = "guardian_embeddings.pkl", *, clip_model=None, processor=None,
+                                 articles: Optional[Sequence[dict]] = None, batch_size: int = 64, device=None,
+                                 val_accuracy=None, vault_dir: Optional[str] = None, rows_per_shard: int = 1 << 20) -> dict:
+    """Batched form of the reference's vault writer (train_clip_detective.py:457-607).
+
+    The reference encodes ONE article per CLIP forward; this encodes `batch_size` at a time (the encoders stay PyTorch
+    producers) and writes the same database: keys article_ids / text_contents / image_paths / image_embeddings /
+    text_embeddings / metadata{model_path,total_articles,embedding_dim,val_accuracy}, rows L2-normalised (:556-557),
+    the pickle at `output_file` plus `<output>_summary.json`; with `vault_dir` also the sharded raw directory of this
+    module.  Articles whose image cannot be opened are reported and skipped, as in the reference (:589-591).
+    clip_model: anything callable as model(input_ids=..., pixel_values=..., ...) -> .image_embeds / .text_embeds
+    (a CLIPModel, or the reference's CLIPDetective.clip); by default loaded from the reference's paths."""
+    import torch
+    from PIL import Image
+    print("\n" + "=" * 60 + "\nGenerating Embeddings Database\n" + "=" * 60)
+    if clip_model is None or processor is None:
+        from transformers import CLIPModel, CLIPProcessor
+        clip_dir = r"C:\Users\Lenovo\OneDrive\Desktop\hack\models\clip-vit-b32"
+        processor = processor or CLIPProcessor.from_pretrained(clip_dir)
+        if clip_model is None:
+            clip_model = CLIPModel.from_pretrained(clip_dir)
+            ckpt = torch.load(model_path, map_location="cpu", weights_only=False)
+            clip_model.load_state_dict({k[len("clip."):]: v for k, v in ckpt["model_state_dict"].items() if k.startswith("clip.")},
+                                       strict=False)
+            val_accuracy = ckpt.get("val_accuracy", val_accuracy)
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
+    if hasattr(clip_model, "to"):
+        clip_model = clip_model.to(device)
+    if hasattr(clip_model, "eval"):
+        clip_model.eval()
+    if articles is None:
+        with open(json_file, "r", encoding="utf-8") as fh:
+            articles = json.load(fh)
+    print(f"Found {len(articles)} articles")
+    db = {"article_ids": [], "text_contents": [], "image_paths": [], "image_embeddings": [], "text_embeddings": [],
+          "metadata": {"model_path": model_path, "total_articles": len(articles), "embedding_dim": None, "val_accuracy": val_accuracy}}
+    with torch.no_grad():
+        for b0 in range(0, len(articles), batch_size):
+            batch, images = [], []
+            for article in articles[b0:b0 + batch_size]:
+                try:
+                    images.append(Image.open(article["image_local_path"]).convert("RGB"))
+                    batch.append(article)
+                except Exception as e:                       # the reference skips the article and goes on
+                    print(f"\nError processing {article['article_id']}: {e}")
+            if not batch:
+                continue
+            inputs = processor(text=[a["text_content"] for a in batch], images=images, return_tensors="pt", padding=True,
+                               truncation=True, max_length=77)
+            inputs = {k: v.to(device) for k, v in inputs.items()}
+            out = clip_model(**inputs, return_dict=True)
+            img = out.image_embeds.float().cpu().numpy()
+            txt = out.text_embeds.float().cpu().numpy()
+            img = img / np.linalg.norm(img, axis=1, keepdims=True)       # :556-557, row-wise
+            txt = txt / np.linalg.norm(txt, axis=1, keepdims=True)
+            db["article_ids"] += [a["article_id"] for a in batch]
+            db["text_contents"] += [a["text_content"] for a in batch]
+            db["image_paths"] += [a["image_local_path"] for a in batch]
+            db["image_embeddings"].append(img)
+            db["text_embeddings"].append(txt)
+    dim = 512
+    db["image_embeddings"] = np.concatenate(db["image_embeddings"]) if db["image_embeddings"] else np.zeros((0, dim), np.float32)
+    db["text_embeddings"] = np.concatenate(db["text_embeddings"]) if db["text_embeddings"] else np.zeros((0, dim), np.float32)
+    db["metadata"]["embedding_dim"] = int(db["image_embeddings"].shape[1])
+    print(f"\n✓ Generated embeddings for {len(db['article_ids'])} articles")
+    with open(output_file, "wb") as fh:
+        pickle.dump(db, fh)
+    size_mb = os.path.getsize(output_file) / 1e6
+    summary = {"total_articles": len(db["article_ids"]), "embedding_dimension": db["metadata"]["embedding_dim"],
+               "model_val_accuracy": db["metadata"]["val_accuracy"], "database_size_mb": size_mb,
+               "sample_articles": db["article_ids"][:5]}
+    with open(output_file.replace(".pkl", "_summary.json"), "w", encoding="utf-8") as fh:
+        json.dump(summary, fh, indent=2)
+    if vault_dir is not None:
+        _, meta = read_vault_dict(db)
+        save_vault_dir(vault_dir, db["image_embeddings"], meta, rows_per_shard=rows_per_shard, source=output_file)
+    print(f"✓ Saved embeddings database ({size_mb:.2f} MB)")
+    return db

@@ -47,7 +47,7 @@ class _Batch(dict):
 
 
 class FakeClipProcessor:
-    def __call__(self, text=None, images=None, return_tensors="pt", padding=True, truncation=False):
+    def __call__(self, text=None, images=None, return_tensors="pt", padding=True, truncation=False, max_length=None):
         out = _Batch()
         if text is not None:
             out["input_ids"] = torch.tensor([[id_of_text(t)] for t in text], dtype=torch.long)

@@ -296,7 +296,76 @@ def gen_similar():
           out["text"][1][0]["similarity"])
 
 
+def gen_writer():
+    """generate_embeddings_database (train_clip_detective.py:457-607), SURVEY.md 8f rank 3: the REFERENCE'S OWN writer
+    run over 40 fake articles (one of them with a missing image); processor / model / checkpoint are the fakes, the
+    per-article loop, the normalisation (:556-557) and the pickle layout are the reference's."""
+    import pickle
+    import tempfile
+    import types
+    if "optuna" not in sys.modules:
+        opt = types.ModuleType("optuna")
+        opt.trial = types.ModuleType("optuna.trial")
+        opt.trial.TrialState = object
+        sys.modules["optuna"], sys.modules["optuna.trial"] = opt, opt.trial
+    with contextlib.redirect_stdout(io.StringIO()):
+        import train_clip_detective as ref_tc
+    n = 40
+    g = np.random.default_rng(80)
+    img_t = (g.standard_normal((n, 512)) * g.uniform(0.2, 6, (n, 1))).astype(np.float32)
+    txt_t = (g.standard_normal((n, 512)) * g.uniform(0.2, 6, (n, 1))).astype(np.float32)
+
+    class FakeDetective(torch.nn.Module):
+        def __init__(self, *a, **kw):
+            super().__init__()
+            self.clip = fakes.FakeClipModel(img_t, txt_t)
+
+        def load_state_dict(self, *a, **kw):
+            return None
+
+        def forward(self, inputs):
+            return self.clip(**inputs, return_dict=True)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        arts = []
+        for i in range(n):
+            path = os.path.join(tmp, f"a{i}.png")
+            if i != 17:                                   # article 17: image missing -> skipped by the writer
+                fakes.image_for_id(i).save(path)
+            arts.append({"article_id": f"art-{i}", "text_content": fakes.text_for_id(i) + " body", "image_local_path": path})
+        with open(os.path.join(tmp, "seed.json"), "w") as fh:
+            json.dump(arts, fh)
+        ckpt = os.path.join(tmp, "clip_detective_best.pth")
+        open(ckpt, "wb").close()
+        real = (ref_tc.CLIPProcessor, ref_tc.CLIPDetective, torch.load)
+        ref_tc.CLIPProcessor = types.SimpleNamespace(from_pretrained=lambda *a, **kw: fakes.FakeClipProcessor())
+        ref_tc.CLIPDetective = FakeDetective
+        torch.load = lambda *a, **kw: {"model_state_dict": {}, "epoch": 3, "val_accuracy": 0.875}
+        try:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                db = quiet(ref_tc.generate_embeddings_database, model_path=ckpt, json_file=os.path.join(tmp, "seed.json"),
+                           output_file=os.path.join(tmp, "out.pkl"))
+            with open(os.path.join(tmp, "out.pkl"), "rb") as fh:
+                on_disk = pickle.load(fh)
+            with open(os.path.join(tmp, "out_summary.json")) as fh:
+                summary = json.load(fh)
+        finally:
+            ref_tc.CLIPProcessor, ref_tc.CLIPDetective, torch.load = real
+    assert np.array_equal(db["image_embeddings"], on_disk["image_embeddings"])
+    np.savez_compressed(os.path.join(HERE, "writer.npz"), image_table=img_t, text_table=txt_t,
+                        image_embeddings=db["image_embeddings"], text_embeddings=db["text_embeddings"])
+    with open(os.path.join(HERE, "writer_cases.json"), "w") as fh:
+        json.dump({"n_articles": n, "missing": 17, "article_ids": db["article_ids"], "text_contents": db["text_contents"],
+                   "image_names": [os.path.basename(p) for p in db["image_paths"]],
+                   "metadata": {k: v for k, v in db["metadata"].items() if k != "model_path"},
+                   "summary": {k: v for k, v in summary.items() if k != "database_size_mb"}}, fh)
+    print("writer.npz", db["image_embeddings"].shape, db["image_embeddings"].dtype, "val_acc", db["metadata"]["val_accuracy"])
+
+
 if __name__ == "__main__":
+    gen_writer()
     gen_similar()
     gen_cosine()
     gen_vault()

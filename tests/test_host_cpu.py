@@ -338,3 +338,52 @@ def test_every_entry_point_rejects_a_null_handle():
     for code, text in ((0, b"ok"), (-1, b"bad argument"), (-2, b"CUDA error"), (-4, b"no CUDA device"), (-5, b"unsupported"),
                        (-6, b"out of device memory"), (-99, b"unknown status")):
         assert lib.mmf_status_string(code) == text
+
+
+def test_batched_vault_writer_matches_reference_writer(tmp_path, capsys):
+    """8f rank 3: vault_io.generate_embeddings_database (batched CLIP forwards) writes the database the reference's
+    one-article-at-a-time writer produced (tests/golden/writer.*: output of train_clip_detective.
+    generate_embeddings_database itself, run over fake articles); the skipped article, the key set, the summary file and
+    the sharded directory are checked too.  Runs on the CPU: the encoders are producers, not the hot path."""
+    import json
+    import pickle
+    sys_path = os.path.join(ROOT, "tests")
+    import sys
+    if sys_path not in sys.path:
+        sys.path.insert(0, sys_path)
+    import fakes
+    from mmf_b200 import vault_io
+    g = np.load(os.path.join(ROOT, "tests", "golden", "writer.npz"))
+    with open(os.path.join(ROOT, "tests", "golden", "writer_cases.json")) as fh:
+        c = json.load(fh)
+    arts = []
+    for i in range(c["n_articles"]):
+        path = tmp_path / f"a{i}.png"
+        if i != c["missing"]:
+            fakes.image_for_id(i).save(path)
+        arts.append({"article_id": f"art-{i}", "text_content": fakes.text_for_id(i) + " body", "image_local_path": str(path)})
+    out = tmp_path / "guardian_embeddings.pkl"
+    for batch_size in (1, 7, 64):
+        db = vault_io.generate_embeddings_database(model_path="clip_detective_best.pth", output_file=str(out), articles=arts,
+                                                   clip_model=fakes.FakeClipModel(g["image_table"], g["text_table"]),
+                                                   processor=fakes.FakeClipProcessor(), batch_size=batch_size, device="cpu",
+                                                   val_accuracy=0.875, vault_dir=str(tmp_path / f"vault{batch_size}"), rows_per_shard=16)
+        assert list(db) == ["article_ids", "text_contents", "image_paths", "image_embeddings", "text_embeddings", "metadata"]
+        assert db["article_ids"] == c["article_ids"] and db["text_contents"] == c["text_contents"]
+        assert [os.path.basename(p) for p in db["image_paths"]] == c["image_names"]
+        for key in ("image_embeddings", "text_embeddings"):
+            assert db[key].dtype == g[key].dtype and np.allclose(db[key], g[key], atol=2e-7), key     # row-wise vs 1-D norm: <= 1 ulp
+        assert {k: v for k, v in db["metadata"].items() if k != "model_path"} == c["metadata"]
+        with open(out, "rb") as fh:
+            disk = pickle.load(fh)
+        assert np.array_equal(disk["image_embeddings"], db["image_embeddings"]) and disk["article_ids"] == db["article_ids"]
+        with open(str(out).replace(".pkl", "_summary.json")) as fh:
+            summary = json.load(fh)
+        assert {k: v for k, v in summary.items() if k != "database_size_mb"} == c["summary"]
+        rows, off, total = vault_io.open_vault_dir(str(tmp_path / f"vault{batch_size}"), 0, 1)
+        assert (off, total) == (0, len(c["article_ids"])) and np.array_equal(rows, db["image_embeddings"])
+        assert vault_io.read_metadata(str(tmp_path / f"vault{batch_size}"))[0]["title"] == c["text_contents"][0]
+    assert f"Error processing art-{c['missing']}" in capsys.readouterr().out
+    # the database is readable by the reference-format reader and searchable as a vault
+    emb, meta = mmf_b200.read_vault_dict(db)
+    assert emb is db["image_embeddings"] and meta[0]["url"] == db["image_paths"][0] and meta[0]["date"] == "N/A"
