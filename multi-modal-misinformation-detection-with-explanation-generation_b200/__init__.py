@@ -13,3 +13,4 @@ from .pipeline import score_batch  # noqa: F401
 from .forensics import MisinfoForensics, MultiModalMisinfoDetector  # noqa: F401
 from .clip_similarity_engine import CLIPSimilarityEngine  # noqa: F401
 from .similar_articles import search_similar_articles  # noqa: F401
+from .fusion_data import FusionTrainingDataset  # noqa: F401

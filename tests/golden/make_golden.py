@@ -364,7 +364,40 @@ def gen_writer():
     print("writer.npz", db["image_embeddings"].shape, db["image_embeddings"].dtype, "val_acc", db["metadata"]["val_accuracy"])
 
 
+def gen_fusion_dataset():
+    """FusionTrainingDataset (train_fusion_judge.py:24-104), SURVEY.md 8f rank 1: the REFERENCE'S OWN dataset class over
+    the reference MisinfoForensics object of gen_analyze (fake producers), one CSV row per sample, one image missing."""
+    import tempfile
+    with contextlib.redirect_stdout(io.StringIO()):
+        import train_fusion_judge as ref_tf
+    g = np.load(os.path.join(HERE, "analyze_inputs.npz"))
+    with open(os.path.join(HERE, "analyze_cases.json")) as fh:
+        cases = json.load(fh)
+    det = fakes.FakeDetector(g["ai"], g["misinfo"], g["deepfake"], fusion_seed=5)
+    f = make_reference_forensics(g["image_table"], g["text_table"], g["vault"], cases["metadata"], det)
+    n = len(g["ai"])
+    with tempfile.TemporaryDirectory() as tmp:
+        rows = []
+        for i in range(n):
+            path = os.path.join(tmp, f"s{i}.png")
+            if i != 5:
+                fakes.image_for_id(i).save(path)
+            rows.append((fakes.text_for_id(i), path, i % 2))
+        csv = os.path.join(tmp, "Final_Fusion_Train.csv")
+        with open(csv, "w") as fh:
+            fh.write("text,image_path,label\n" + "".join(f"{t},{p},{lab}\n" for t, p, lab in rows))
+        ds = quiet(ref_tf.FusionTrainingDataset, csv, f)
+        items = [quiet(ds.__getitem__, i) for i in range(len(ds))]
+        ds2 = quiet(ref_tf.FusionTrainingDataset, csv, f, 7)
+    scores = torch.stack([it["scores"] for it in items]).numpy()
+    labels = torch.stack([it["label"] for it in items]).numpy()
+    assert scores.dtype == np.float32 and labels.dtype == np.int64 and len(ds2) == 7 and not scores[5].any()
+    np.savez_compressed(os.path.join(HERE, "fusion_dataset.npz"), scores=scores, labels=labels, missing=np.array([5]))
+    print("fusion_dataset.npz", scores.shape, "mean", scores.mean(0).round(4))
+
+
 if __name__ == "__main__":
+    gen_fusion_dataset()
     gen_writer()
     gen_similar()
     gen_cosine()

@@ -192,3 +192,35 @@ def test_search_similar_articles_host_logic(tmp_path, capsys):
         mmf_b200.search_similar_articles(search_mode="text", embeddings_db=db, **common)
     assert "Top 5 similar articles" in capsys.readouterr().out
     json.dumps(got)
+
+
+def test_fusion_training_dataset_host_logic(tmp_path, capsys):
+    """8f rank 1: the cached (M,5) score matrix == what the reference's FusionTrainingDataset.__getitem__ computes per
+    sample (tests/golden/fusion_dataset.npz: output of train_fusion_judge.FusionTrainingDataset itself); missing image
+    -> zeros, max_samples, item schema, and a DataLoader batch like the reference trainer's"""
+    g, cases = _load_analyze_fixture()
+    want = np.load(os.path.join(GOLDEN, "fusion_dataset.npz"))
+    f = _forensics(g, cases)
+    n = len(g["ai"])
+    rows = []
+    for i in range(n):
+        p = tmp_path / f"s{i}.png"
+        if i != int(want["missing"][0]):
+            fakes.image_for_id(i).save(p)
+        rows.append((fakes.text_for_id(i), str(p), i % 2))
+    csv = tmp_path / "Final_Fusion_Train.csv"
+    csv.write_text("text,image_path,label\n" + "".join(f"{t},{p},{lab}\n" for t, p, lab in rows))
+    for batch_size in (256, 5):
+        ds = mmf_b200.FusionTrainingDataset(str(csv), f, batch_size=batch_size)
+        assert len(ds) == n
+        items = [ds[i] for i in range(n)]
+        scores = torch.stack([it["scores"] for it in items]).numpy()
+        assert scores.dtype == np.float32 and items[0]["label"].dtype == torch.long and items[0]["scores"].shape == (5,)
+        assert np.allclose(scores, want["scores"], atol=FP32_TOL) and not scores[int(want["missing"][0])].any()
+        assert np.array_equal(torch.stack([it["label"] for it in items]).numpy(), want["labels"])
+    assert "Image not found" in capsys.readouterr().out
+    assert len(mmf_b200.FusionTrainingDataset(str(csv), f, max_samples=7)) == 7
+    batch = next(iter(torch.utils.data.DataLoader(ds, batch_size=16, shuffle=False)))
+    assert batch["scores"].shape == (16, 5) and batch["label"].shape == (16,)
+    logits = f.detector.forward_fusion(batch["scores"])            # what the reference trainer does with it (:221)
+    assert logits.shape == (16, 2)
