@@ -1,0 +1,133 @@
+"""bench.py is what the driver runs; a Python-level slip in it costs the round's measurement.  This dry run executes
+bench.main() on the CPU with the CUDA-facing pieces swapped for stand-ins (the engine is the oracle-backed test double
+of tests/cpu_engine.py, torch.cuda is a small fake, vault rows are cut down with --rows), and checks the JSON line it
+prints against the contract: keys, units, the roofline / cpu_baseline / e2e objects.  No number it produces means
+anything -- only that every code path of the harness runs and the line is well-formed."""
+import importlib.util
+import json
+import os
+import sys
+import time
+import types
+
+import pytest
+import torch
+
+from cpu_engine import OracleEngine
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _Event:
+    def __init__(self, enable_timing=False):
+        self.t = 0.0
+
+    def record(self):
+        self.t = time.perf_counter()
+
+    def elapsed_time(self, other):
+        return max((other.t - self.t) * 1e3, 1e-3)
+
+
+class _CountingEngine(OracleEngine):
+    """the double plus the launch counter bench.py reads"""
+
+    def __init__(self, device=None):
+        super().__init__()
+        self._n = 0
+
+    @property
+    def launch_count(self):
+        self._n += 3
+        return self._n
+
+    @launch_count.setter
+    def launch_count(self, v):
+        pass
+
+
+def _load_bench(monkeypatch):
+    spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cpu = torch.device("cpu")
+    fake_cuda = types.SimpleNamespace(set_device=lambda *a, **k: None, synchronize=lambda *a, **k: None, Event=_Event,
+                                      is_available=lambda: False)
+    real_randn, real_generator = torch.randn, torch.Generator
+
+    class _TorchProxy:
+        """torch, with 'cuda' devices mapped to the CPU"""
+        cuda = fake_cuda
+
+        def __getattr__(self, name):
+            return getattr(torch, name)
+
+        @staticmethod
+        def device(*a, **k):
+            return cpu
+
+        @staticmethod
+        def Generator(device=None):
+            return real_generator()
+
+        @staticmethod
+        def randn(*a, device=None, **k):
+            return real_randn(*a, **k)
+
+    monkeypatch.setattr(bench, "torch", _TorchProxy())
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+    import mmf_b200
+    monkeypatch.setattr(mmf_b200, "Engine", _CountingEngine)
+    return bench
+
+
+def _run(bench, monkeypatch, capsys, argv):
+    monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, lines
+    return json.loads(lines[0])
+
+
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+             "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"}
+
+
+@pytest.mark.parametrize("workload", ["c2", "c3", "c4"])
+def test_bench_line_is_well_formed(monkeypatch, capsys, workload):
+    bench = _load_bench(monkeypatch)
+    rows = {"c2": 3000, "c3": 3000, "c4": 2500}[workload]
+    if workload == "c3":                                  # keep the 1000-query latency sweep cheap on the CPU
+        real_search = OracleEngine.vault_search
+        monkeypatch.setattr(_CountingEngine, "vault_search", lambda self, q, *a, **k: real_search(self, q, *a, **k))
+    d = _run(bench, monkeypatch, capsys, ["--workload", workload, "--rows", str(rows), "--steps", "2", "--warmup", "3"])
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "vault queries/s" and d["unit"] == "queries/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["scaling"] == ("strong" if workload == "c4" else "weak") and d["dtype"] == ("bf16" if workload == "c4" else "f32")
+    assert set(d["config"]) >= {"workload", "queries_per_step", "vault_rows_total", "vault_rows_per_gpu", "top_k", "parallelism", "l2"}
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
+    assert r["bound"] == ("tensor" if workload == "c4" else "hbm") and r["unit"] == ("TFLOP/s" if workload == "c4" else "GB/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is None        # --rows override: no ncu traffic claimed
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c and "host" in c and "batched_restatement" in c
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == "queries/s"
+    assert d["gpu_launches"] > 0 and "reasons" in d["clocks"]
+    if workload == "c2":
+        assert r["variant"].startswith("screened") and r["mma_passes"] == 1 and r["bytes_streamed_per_launch"] == rows * 512 * 2
+    if workload == "c3":
+        lat = d["latency"]
+        assert lat["queries"] == 1000 and lat["p50"] <= lat["p90"] <= lat["p99"] <= lat["max"]
+
+
+def test_bench_reference_arm_line(monkeypatch, capsys):
+    bench = _load_bench(monkeypatch)
+    d = _run(bench, monkeypatch, capsys, ["--impl", "reference", "--rows", "4000", "--steps", "2", "--warmup", "1"])
+    assert d["impl"] == "reference" and d["metric"] == "vault queries/s" and d["unit"] == "queries/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert set(d["config"]) >= {"workload", "queries_per_step", "vault_rows_total", "top_k", "parallelism"}
