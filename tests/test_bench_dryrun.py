@@ -45,6 +45,13 @@ class _CountingEngine(OracleEngine):
     def launch_count(self, v):
         pass
 
+    def score_batch_host(self, text, image, head, modality=None, top_k=5, threshold=0.85, algo="auto"):
+        """stand-in for Engine.score_batch_host (mmf_score_batch_host): same dict, numpy values"""
+        import mmf_b200
+        vault = types.SimpleNamespace(search=lambda q, k, thr, a: self.vault_search(q, k, thr, a)) if self._vault is not None else None
+        out = mmf_b200.score_batch(self, vault, text, image, head, modality, top_k, algo)
+        return {k: v.numpy() for k, v in out.items()}
+
 
 def _load_bench(monkeypatch):
     spec = importlib.util.spec_from_file_location("bench_under_test", os.path.join(ROOT, "bench.py"))
@@ -131,3 +138,11 @@ def test_bench_reference_arm_line(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert set(d["config"]) >= {"workload", "queries_per_step", "vault_rows_total", "top_k", "parallelism"}
+
+
+def test_bench_e2e_host_api_branch(monkeypatch, capsys):
+    """--e2e-api host: the single-call host entry (not yet run on a GPU) is at least wired correctly in the harness"""
+    bench = _load_bench(monkeypatch)
+    d = _run(bench, monkeypatch, capsys, ["--rows", "3000", "--steps", "2", "--warmup", "3", "--e2e-api", "host", "--no-cpu-baseline"])
+    assert d["cpu_baseline"] is None and d["e2e"]["value"] > 0 and "score_batch_host" in d["e2e"]["api"]
+    assert d["e2e"]["d2h_bytes_per_step"] == 256 * (4 + 2 * 4 + 10 * 4 + 10 * 8 + 4 + 4 + 5 * 4 + 4)      # verdict, probs, top-10 scores / rows, sim, disc, x, conf
