@@ -146,3 +146,16 @@ def test_bench_e2e_host_api_branch(monkeypatch, capsys):
     d = _run(bench, monkeypatch, capsys, ["--rows", "3000", "--steps", "2", "--warmup", "3", "--e2e-api", "host", "--no-cpu-baseline"])
     assert d["cpu_baseline"] is None and d["e2e"]["value"] > 0 and "score_batch_host" in d["e2e"]["api"]
     assert d["e2e"]["d2h_bytes_per_step"] == 256 * (4 + 2 * 4 + 10 * 4 + 10 * 8 + 4 + 4 + 5 * 4 + 4)      # verdict, probs, top-10 scores / rows, sim, disc, x, conf
+
+
+def test_graft_entry_smoke_logic(monkeypatch, capsys):
+    """__graft_entry__.smoke() -- the driver's first GPU call -- with the engine swapped for the test double: its own
+    Python (inputs, the oracle comparisons, the final print) must run; the real thing needs the B200"""
+    spec = importlib.util.spec_from_file_location("graft_entry_under_test", os.path.join(ROOT, "__graft_entry__.py"))
+    ge = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ge)
+    import mmf_b200
+    monkeypatch.setattr(mmf_b200, "Engine", _CountingEngine)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    ge.smoke()
+    assert "smoke ok" in capsys.readouterr().out
