@@ -25,6 +25,10 @@ from mmf_b200 import synth  # noqa: E402
 
 @pytest.fixture(scope="module")
 def eng():
+    if os.environ.get("MMF_TEST_DOUBLE") == "1":          # CPU check of THIS FILE's own Python only (tests/cpu_engine.py)
+        from cpu_engine import OracleEngine
+        yield OracleEngine()
+        return
     e = mmf_b200.Engine("cuda:0")
     yield e
     e.close()
