@@ -22,6 +22,9 @@ pytestmark = [pytest.mark.gpu,
 import mmf_b200  # noqa: E402
 from mmf_b200 import synth  # noqa: E402
 
+DOUBLE = os.environ.get("MMF_TEST_DOUBLE") == "1"     # CPU check of this file's own Python (see the eng fixture)
+DEV = "cpu" if DOUBLE else "cuda"
+
 
 @pytest.fixture(scope="module")
 def eng():
@@ -111,10 +114,10 @@ def test_screened_search_is_exact(eng, n_rows, nq, k):
     error band.  The result must be the exact top-k: bit-identical to the streaming kernel (same re-scoring
     arithmetic), and within the fp32 tolerance of the oracle."""
     if n_rows >= 1_000_000:
-        g = torch.Generator(device="cuda").manual_seed(3)
-        vault = torch.randn(n_rows, 512, device="cuda", generator=g)
-        q = torch.randn(nq, 512, device="cuda", generator=g)
-        q[:32] = vault[torch.arange(32, device="cuda") * 31_001] + 0.3 * q[:32]
+        g = torch.Generator(device=DEV).manual_seed(3)
+        vault = torch.randn(n_rows, 512, device=DEV, generator=g)
+        q = torch.randn(nq, 512, device=DEV, generator=g)
+        q[:32] = vault[torch.arange(32, device=DEV) * 31_001] + 0.3 * q[:32]
     else:
         vault = synth.vault_rows(n_rows, seed=n_rows + 1) * np.random.default_rng(2).uniform(0.1, 5, (n_rows, 1)).astype(np.float32)
         q, _, _ = synth.queries(nq, n_rows, seed=nq + 11, plant_frac=0.4, vault_seed=n_rows + 1)
@@ -188,7 +191,7 @@ def test_peer_exchange_single_rank_loopback(eng):
     q, _, _ = synth.queries(nq, n_rows, seed=52, plant_frac=0.5, vault_seed=51)
     eng.vault_load(vault, mode="fp32")
     need = eng.exchange_layout(1, nq, 100)
-    buf = torch.zeros(need // 8 + 16, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(need // 8 + 16, dtype=torch.int64, device=DEV)
     eng.exchange_attach(0, 1, [buf.data_ptr()], buf.numel() * 8)
     try:
         for k in (10, 100, 5):
@@ -206,14 +209,16 @@ def test_c4_shard_size_properties(eng):
     """BASELINE config C4 at the size one rank sees on 8 GPUs (4096 queries x 1.25 M bf16 rows, top-100), through
     size-independent properties: planted rows first at their cosine, scores sorted, a query scaled is the same
     query, a 2-way row split + candidate merge equals the unsplit search bit for bit, both bound variants agree."""
+    if DOUBLE:
+        pytest.skip("4096 queries x 1.25 M rows is not a CPU-sized problem")
     n_rows, nq, k = 1_250_000, 4096, 100
-    g = torch.Generator(device="cuda").manual_seed(11)
-    vault = torch.randn(n_rows, 512, device="cuda", generator=g)
-    q = torch.randn(nq, 512, device="cuda", generator=g)
-    pick = torch.randint(0, n_rows, (400,), device="cuda", generator=g)
+    g = torch.Generator(device=DEV).manual_seed(11)
+    vault = torch.randn(n_rows, 512, device=DEV, generator=g)
+    q = torch.randn(nq, 512, device=DEV, generator=g)
+    pick = torch.randint(0, n_rows, (400,), device=DEV, generator=g)
     vn = torch.nn.functional.normalize(vault[pick], dim=1)
     noise = torch.nn.functional.normalize(q[:400] - (q[:400] * vn).sum(1, keepdim=True) * vn, dim=1)
-    cosv = torch.tensor([0.8, 0.849, 0.851, 0.9, 0.99], device="cuda").repeat(80)
+    cosv = torch.tensor([0.8, 0.849, 0.851, 0.9, 0.99], device=DEV).repeat(80)
     q[:400] = (cosv[:, None] * vn + torch.sqrt(1 - cosv ** 2)[:, None] * noise) * 3.0
     eng.vault_load(vault, mode="bf16")
     scores, rows, disc = eng.vault_search(q, k)
@@ -243,9 +248,9 @@ def test_c4_shard_size_properties(eng):
                                          (300000, 8, 16), (1_000_000, 1, 10)])
 def test_screened_streaming_kernel_is_exact(eng, n_rows, nq, k):
     """MMF_STREAM_SCREEN=1 (batch-1 path reads only the hi planes, re-scores the band exactly) == exact streaming kernel"""
-    g = torch.Generator(device="cuda").manual_seed(n_rows + nq)
-    vault = torch.randn(n_rows, 512, device="cuda", generator=g) * (0.1 + torch.rand(n_rows, 1, device="cuda", generator=g) * 4)
-    q = torch.randn(nq, 512, device="cuda", generator=g)
+    g = torch.Generator(device=DEV).manual_seed(n_rows + nq)
+    vault = torch.randn(n_rows, 512, device=DEV, generator=g) * (0.1 + torch.rand(n_rows, 1, device=DEV, generator=g) * 4)
+    q = torch.randn(nq, 512, device=DEV, generator=g)
     q[0] = vault[n_rows // 2] * 2 + 0.3 * q[0]
     eng.vault_load(vault, mode="fp32")
     want = [npy(t) for t in eng.vault_search(q, k, algo="stream")]
@@ -273,9 +278,9 @@ def test_screened_streaming_kernel_overflow_and_ties(eng):
 def test_screened_search_experiments_change_nothing(eng, switches):
     """deeper ring / L2 prefetch / lean launch sequence only change HOW the screening pass runs"""
     for n_rows, nq, k in ((40000, 257, 10), (5000, 16, 10), (500000, 256, 5)):
-        g = torch.Generator(device="cuda").manual_seed(n_rows)
-        vault = torch.randn(n_rows, 512, device="cuda", generator=g)
-        q = torch.randn(nq, 512, device="cuda", generator=g)
+        g = torch.Generator(device=DEV).manual_seed(n_rows)
+        vault = torch.randn(n_rows, 512, device=DEV, generator=g)
+        q = torch.randn(nq, 512, device=DEV, generator=g)
         q[:8] = vault[:8] + 0.2 * q[:8]
         eng.vault_load(vault, mode="fp32")
         want = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
@@ -297,7 +302,12 @@ def test_search_similar_articles_dropin_on_gpu(tmp_path):
     k = c["top_k"]
     db = {"article_ids": c["article_ids"], "text_contents": c["text_contents"], "image_paths": c["image_paths"],
           "image_embeddings": g["image_embeddings"], "text_embeddings": g["text_embeddings"]}
-    engine = mmf_b200.Engine("cuda:0")
+    if DOUBLE:
+        from cpu_engine import OracleEngine
+        engine = OracleEngine()
+        engine.close = lambda: None
+    else:
+        engine = mmf_b200.Engine("cuda:0")
     common = dict(clip_model=fakes.FakeClipModel(g["image_queries"], g["text_queries"]), processor=fakes.FakeClipProcessor(), engine=engine)
     for i, want in enumerate(c["results"]["text"]):
         got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(i), top_k=k, embeddings_db=db, **common)
