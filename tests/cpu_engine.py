@@ -92,3 +92,14 @@ class OracleEngine:
         rows = np.where(flat != 0, (flat & np.uint64(0xFFFFFFFF)).astype(np.int64), -1)
         disc = np.where(flat[:, 0] != 0, oracle.discrepancy_rule(np.nan_to_num(scores[:, 0], nan=0.0), threshold), 0).astype(np.float32)
         return torch.from_numpy(scores), torch.from_numpy(rows), torch.from_numpy(disc)
+
+    # ---- the one-call host entry (Engine.score_batch_host): same dict, numpy values
+    def score_batch_host(self, text_embeds, image_embeds, head_scores, modality=None, top_k=5,
+                         threshold=oracle.VAULT_THRESHOLD, algo="auto"):
+        import types
+
+        import mmf_b200
+        vault = types.SimpleNamespace(search=lambda q, k, thr, a: self.vault_search(q, k, thr, a)) if self._vault is not None else None
+        out = mmf_b200.score_batch(self, vault, torch.as_tensor(text_embeds), torch.as_tensor(image_embeds),
+                                   torch.as_tensor(head_scores), modality, top_k, algo)
+        return {k: v.numpy() for k, v in out.items()}

@@ -45,12 +45,6 @@ class _CountingEngine(OracleEngine):
     def launch_count(self, v):
         pass
 
-    def score_batch_host(self, text, image, head, modality=None, top_k=5, threshold=0.85, algo="auto"):
-        """stand-in for Engine.score_batch_host (mmf_score_batch_host): same dict, numpy values"""
-        import mmf_b200
-        vault = types.SimpleNamespace(search=lambda q, k, thr, a: self.vault_search(q, k, thr, a)) if self._vault is not None else None
-        out = mmf_b200.score_batch(self, vault, text, image, head, modality, top_k, algo)
-        return {k: v.numpy() for k, v in out.items()}
 
 
 def _load_bench(monkeypatch):

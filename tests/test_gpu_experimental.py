@@ -178,8 +178,8 @@ def test_score_batch_host_equals_score_batch(eng):
             assert np.array_equal(got[key], npy(want[key]), equal_nan=True), key
     # pinned torch tensors in, and no vault loaded -> zero discrepancy / no rows
     eng.vault_unload()
-    got = eng.score_batch_host(torch.from_numpy(text).pin_memory(), torch.from_numpy(q).pin_memory(),
-                               torch.from_numpy(head).pin_memory(), None, k)
+    pin = (lambda t: t) if DOUBLE else (lambda t: t.pin_memory())
+    got = eng.score_batch_host(pin(torch.from_numpy(text)), pin(torch.from_numpy(q)), pin(torch.from_numpy(head)), None, k)
     assert np.all(got["vault_rows"] == -1) and np.all(got["vault_discrepancy"] == 0) and np.all(np.isnan(got["vault_scores"]))
 
 
