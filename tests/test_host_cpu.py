@@ -387,3 +387,26 @@ def test_batched_vault_writer_matches_reference_writer(tmp_path, capsys):
     # the database is readable by the reference-format reader and searchable as a vault
     emb, meta = mmf_b200.read_vault_dict(db)
     assert emb is db["image_embeddings"] and meta[0]["url"] == db["image_paths"][0] and meta[0]["date"] == "N/A"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """the boundary is a C ABI: include/mmf_b200.h must compile as C99 (no C++-isms) and a plain C program must link
+    against libmmf_b200.so and call the handle-free entry points"""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "mmf_b200.h")], check=True)
+    src = tmp_path / "abi.c"
+    src.write_text('#include "mmf_b200.h"\n#include <stdio.h>\nint main(void) {\n  mmf_handle* h = 0;\n  int64_t units; int pairs, cg;\n'
+                   '  int rc = mmf_mma_plan_check(256, 1000000, 148, &units, &pairs, &cg);\n'
+                   '  printf("%s|%d|%d|%lld|%d|%d|%s\\n", mmf_version(), mmf_arch(), rc, (long long)units, pairs, cg, '
+                   'mmf_status_string(mmf_vault_unload(h)));\n  return 0;\n}\n')
+    libdir = os.path.dirname(_lib.library_path())
+    exe = tmp_path / "abi"
+    subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lmmf_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().split("|")
+    assert out[0].startswith("mmf_b200") and out[1:] == ["100", "0", "7813", "74", "2", "bad argument"]
