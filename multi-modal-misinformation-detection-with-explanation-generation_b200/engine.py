@@ -173,7 +173,7 @@ class Engine:
         results as numpy arrays in host memory -- one D2H and one synchronisation instead of one per tensor.
         Same values as mmf_b200.score_batch.  Needs the fusion weights; a vault is optional."""
         def host(x, cols, dt):
-            a = x.numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+            a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)   # a CPU tensor is not copied
             a = np.ascontiguousarray(a, dtype=dt).reshape(-1, cols) if cols else np.ascontiguousarray(a, dtype=dt).reshape(-1)
             return a
         t, im, hs = host(text_embeds, 512, np.float32), host(image_embeds, 512, np.float32), host(head_scores, 3, np.float32)
