@@ -63,6 +63,47 @@ def _features(x):
     return x if torch.is_tensor(x) else x.pooler_output
 
 
+def _load_checked(module: nn.Module, state: dict, what: str) -> None:
+    """load_state_dict(strict=False) that SAYS when nothing matched (strict=False never raises for that)."""
+    res = module.load_state_dict(state, strict=False)
+    own = set(module.state_dict().keys())
+    if not state or own.issubset(set(res.missing_keys)):
+        print(f"  ⚠ {what}: no parameter of the checkpoint matched -- weights stay as initialised")
+
+
+def load_individual_weights(detector: nn.Module, ai_head_weights: str, misinfo_head_weights: str,
+                            efficientnet_weights: str) -> None:
+    """Per-branch fallback of the reference (misinfo_forensics.py:260-304): the head checkpoints are
+    {'model_state_dict': {'ai_head.0.weight', ...}, 'epoch', ...} -- filter by branch name, strip the prefix;
+    EfficientNet is either that form (prefix 'efficientnet.') or a raw state_dict (whole net, else classifier only).
+    (The reference also tries `clip_detective_best.pth` here, but at that point its CLIP model does not exist yet,
+    the attempt always ends in its except branch and from_pretrained follows -- so nothing to mirror.)"""
+    for path, branch, target in ((ai_head_weights, "ai_head", detector.ai_head),
+                                 (misinfo_head_weights, "misinfo_head", detector.misinfo_head)):
+        if os.path.exists(path):
+            print(f"Loading {branch} from {path}...")
+            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            state = {k.replace(branch + ".", ""): v for k, v in ckpt["model_state_dict"].items() if branch in k}
+            _load_checked(target, state, path)
+            print(f"  ✓ Loaded from epoch {ckpt.get('epoch', 'N/A')}")
+    if os.path.exists(efficientnet_weights):
+        print(f"Loading EfficientNet from {efficientnet_weights}...")
+        ckpt = torch.load(efficientnet_weights, map_location="cpu", weights_only=False)
+        if isinstance(ckpt, dict) and "model_state_dict" in ckpt:
+            state = {k.replace("efficientnet.", ""): v for k, v in ckpt["model_state_dict"].items() if "efficientnet" in k}
+            _load_checked(detector.efficientnet, state, efficientnet_weights)
+            print(f"  ✓ Loaded from epoch {ckpt.get('epoch', 'N/A')}")
+        else:
+            try:
+                _load_checked(detector.efficientnet, ckpt, efficientnet_weights)
+                print("  ✓ Loaded weights successfully")
+            except RuntimeError:
+                cls = {k: v for k, v in ckpt.items() if "classifier" in k}
+                if cls:
+                    detector.efficientnet.classifier.load_state_dict(cls, strict=False)
+                    print("  ✓ Loaded classifier head")
+
+
 class MisinfoForensics:
     def __init__(
         self,
@@ -143,7 +184,7 @@ class MisinfoForensics:
 
     # ------------------------------------------------------------------ weights
     def _load_detector_weights(self, detector, fusion_weights, ai_w, mis_w, eff_w):
-        """full_model_state_dict first (misinfo_forensics.py:175-197), else per-branch files."""
+        """full_model_state_dict first (misinfo_forensics.py:175-197), else per-branch files (:260-304)."""
         if os.path.exists(fusion_weights):
             try:
                 ckpt = torch.load(fusion_weights, map_location="cpu", weights_only=False)
@@ -152,15 +193,8 @@ class MisinfoForensics:
                 return
             except Exception as e:
                 print(f"  ⚠ Error loading fusion weights: {e}")
-        for path, key, target in ((ai_w, "ai_head_state_dict", detector.ai_head),
-                                  (mis_w, "misinfo_head_state_dict", detector.misinfo_head),
-                                  (eff_w, None, detector.efficientnet)):
-            if os.path.exists(path):
-                try:
-                    sd = torch.load(path, map_location="cpu", weights_only=False)
-                    target.load_state_dict(sd[key] if key and key in sd else sd, strict=False)
-                except Exception as e:
-                    print(f"  ⚠ Could not load {path}: {e}")
+                print("  Falling back to individual model loading...")
+        load_individual_weights(detector, ai_w, mis_w, eff_w)
 
     def reload_fusion(self):
         """Re-read detector.fusion_layer into the library (the fusion trainer mutates those
@@ -193,8 +227,10 @@ class MisinfoForensics:
         with torch.no_grad():
             return _features(self.clip_model.get_image_features(**inputs))
 
-    def _clip_text_embed(self, texts: Sequence[str]) -> torch.Tensor:
-        inputs = self.clip_processor(text=list(texts), return_tensors="pt", padding=True, truncation=True).to(self.device)
+    def _clip_text_embed(self, texts: Sequence[str], truncation: bool = True) -> torch.Tensor:
+        """truncation=True is the caption/headline step (misinfo_forensics.py:471-476); the caption/image consistency
+        step does NOT truncate (:386-391: a caption over 77 tokens raises there, and so it does here)."""
+        inputs = self.clip_processor(text=list(texts), return_tensors="pt", padding=True, truncation=truncation).to(self.device)
         with torch.no_grad():
             return _features(self.clip_model.get_text_features(**inputs))
 
@@ -449,7 +485,9 @@ class MisinfoForensics:
         if vis:
             i_emb[vis] = self._clip_image_embed([pils[i] for i in vis]).float()
         if both:
-            t_emb[both] = self._clip_text_embed([texts[i] for i in both]).float()
+            # no truncation, like analyze_consistency: a caption the reference cannot encode raises here too
+            # (FusionTrainingDataset isolates such a sample and serves zeros for it, train_fusion_judge.py:97-99)
+            t_emb[both] = self._clip_text_embed([texts[i] for i in both], truncation=False).float()
         out = self.score_batch(t_emb, i_emb, head, mod, top_k=top_k)
         x = out["scores"].cpu().numpy().astype(np.float64)
         probs, verdict, conf = out["probs"].cpu().numpy(), out["verdict"].cpu().numpy(), out["confidence"].cpu().numpy()

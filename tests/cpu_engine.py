@@ -39,6 +39,13 @@ class OracleEngine:
         self._vault = oracle.vault_normalise(arr.astype(np.float32)).astype(np.float32)   # the library normalises in fp32
         self._row_offset, self.vault_rows, self.vault_mode = int(row_offset), arr.shape[0], mode
 
+    def article_index(self, embeddings_db, key):
+        """search_similar_articles keeps the article database in a PRIVATE handle (similar_articles._article_index);
+        the test double's equivalent: a second OracleEngine, so that this one's resident vault stays untouched."""
+        idx = OracleEngine()
+        idx.vault_load(np.asarray(embeddings_db[key]), mode="fp32")
+        return idx
+
     def vault_unload(self):
         self._vault, self.vault_rows, self.vault_mode = None, 0, None
 

@@ -164,7 +164,9 @@ def test_search_similar_articles_host_logic(tmp_path, capsys):
     db = {"article_ids": c["article_ids"], "text_contents": c["text_contents"], "image_paths": c["image_paths"],
           "image_embeddings": g["image_embeddings"], "text_embeddings": g["text_embeddings"]}
     clip = fakes.FakeClipModel(g["image_queries"], g["text_queries"])
-    common = dict(clip_model=clip, processor=fakes.FakeClipProcessor(), engine=OracleEngine())
+    shared = OracleEngine()
+    shared.vault_load(np.eye(4, 512, dtype=np.float32), mode="fp32")          # a resident Truth Vault that must survive
+    common = dict(clip_model=clip, processor=fakes.FakeClipProcessor(), engine=shared)
     for i, want in enumerate(c["results"]["text"]):
         got = mmf_b200.search_similar_articles(query_text=fakes.text_for_id(i), top_k=k, search_mode="text", embeddings_db=db, **common)
         assert [(r["rank"], r["article_id"], r["text"], r["image_path"]) for r in got] == \
@@ -192,6 +194,7 @@ def test_search_similar_articles_host_logic(tmp_path, capsys):
         mmf_b200.search_similar_articles(search_mode="text", embeddings_db=db, **common)
     assert "Top 5 similar articles" in capsys.readouterr().out
     json.dumps(got)
+    assert shared.vault_rows == 4                                             # the caller's vault is not replaced
 
 
 def test_fusion_training_dataset_host_logic(tmp_path, capsys):
@@ -224,3 +227,39 @@ def test_fusion_training_dataset_host_logic(tmp_path, capsys):
     assert batch["scores"].shape == (16, 5) and batch["label"].shape == (16,)
     logits = f.detector.forward_fusion(batch["scores"])            # what the reference trainer does with it (:221)
     assert logits.shape == (16, 2)
+
+
+def test_individual_weight_files_load_in_the_reference_layout(tmp_path, capsys):
+    """ai_head_best.pth / roberta_detective_best.pth are {'model_state_dict': {'ai_head.0.weight', ...},
+    'epoch': ...}; the reference filters by branch name and strips the prefix (misinfo_forensics.py:270-283), and accepts
+    EfficientNet either as {'model_state_dict': {'efficientnet.…'}} or as a raw state_dict (:286-304)."""
+    from transformers import RobertaConfig, RobertaModel
+    from mmf_b200.forensics import MultiModalMisinfoDetector, load_individual_weights
+    cfg = RobertaConfig(vocab_size=64, hidden_size=32, num_hidden_layers=1, num_attention_heads=2, intermediate_size=64,
+                        max_position_embeddings=40, type_vocab_size=1, pad_token_id=1)
+    torch.manual_seed(11)
+    src = MultiModalMisinfoDetector(roberta=RobertaModel(cfg))          # "trained" weights
+    torch.manual_seed(12)
+    dst = MultiModalMisinfoDetector(roberta=RobertaModel(cfg))          # freshly initialised
+    full = src.state_dict()
+    assert not torch.equal(src.ai_head[0].weight, dst.ai_head[0].weight)
+    ai, mis, eff = (str(tmp_path / n) for n in ("ai_head_best.pth", "roberta_detective_best.pth", "efficientnet_cifake_best.pth"))
+    torch.save({"model_state_dict": {k: v for k, v in full.items() if k.startswith(("roberta.", "ai_head."))}, "epoch": 3}, ai)
+    torch.save({"model_state_dict": {k: v for k, v in full.items() if k.startswith(("roberta.", "misinfo_head."))}, "epoch": 4}, mis)
+    torch.save({"model_state_dict": {k: v for k, v in full.items() if k.startswith("efficientnet.")}, "epoch": 5}, eff)
+    load_individual_weights(dst, ai, mis, eff)
+    for a, b in ((src.ai_head, dst.ai_head), (src.misinfo_head, dst.misinfo_head), (src.efficientnet, dst.efficientnet)):
+        for (ka, va), (kb, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+            assert ka == kb and torch.equal(va, vb), ka
+    out = capsys.readouterr().out
+    assert "epoch 3" in out and "epoch 4" in out and "epoch 5" in out and "no parameter" not in out
+    # raw EfficientNet state_dict form
+    torch.manual_seed(13)
+    dst2 = MultiModalMisinfoDetector(roberta=RobertaModel(cfg))
+    torch.save(src.efficientnet.state_dict(), eff)
+    load_individual_weights(dst2, str(tmp_path / "absent.pth"), str(tmp_path / "absent2.pth"), eff)
+    assert torch.equal(src.efficientnet.classifier[1].weight, dst2.efficientnet.classifier[1].weight)
+    # a checkpoint that matches nothing is reported, not silently ignored
+    torch.save({"model_state_dict": {"something.else": torch.zeros(1)}, "epoch": 0}, ai)
+    load_individual_weights(dst2, ai, str(tmp_path / "absent2.pth"), str(tmp_path / "absent3.pth"))
+    assert "no parameter of the checkpoint matched" in capsys.readouterr().out
