@@ -38,7 +38,8 @@ enum mmf_status {
   MMF_ERR_NOT_LOADED = -3, /* vault / fusion weights not loaded (reference: vault_loaded == False) */
   MMF_ERR_NO_DEVICE = -4,
   MMF_ERR_UNSUPPORTED = -5,
-  MMF_ERR_NOMEM = -6
+  MMF_ERR_NOMEM = -6,
+  MMF_ERR_NCCL = -7 /* the NCCL library is missing or a collective failed (row-sharded search only) */
 };
 
 enum mmf_dtype { MMF_F32 = 0, MMF_F16 = 1, MMF_BF16 = 2, MMF_F64 = 3 };
@@ -118,6 +119,32 @@ int mmf_vault_search_candidates(mmf_handle* h, const float* queries, int64_t n_q
 int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n_queries, int k_in, int top_k,
                    double threshold, float* out_scores, int64_t* out_rows, float* out_discrepancy,
                    mmf_stream_t stream);
+
+/* ---- Row-sharded search with the collective owned by the library -------------------
+ * Sharded form of misinfo_forensics.py:443-450: rank r holds rows [row_offset, row_offset + n_rows) of the vault
+ * (mmf_vault_load), every rank searches its shard, ONE ncclAllGather moves the packed per-shard top-k candidates
+ * (8 B each) over NVLink and every rank merges them -- identical results on every rank, bit-identical to the
+ * unsharded search.  NCCL is bound at run time (dlopen of libnccl.so.2, or $MMF_NCCL_LIB); a process that
+ * already carries one (PyTorch) shares it.
+ * Bootstrap: rank 0 calls mmf_shard_unique_id and hands the MMF_SHARD_ID_BYTES bytes to its peers out of band
+ * (torch.distributed store, MPI, a file ...); then EVERY rank calls mmf_shard_init (collective, blocking).
+ * world == 1 needs no id and no NCCL.  One shard group per handle; mmf_destroy finalises it. */
+#define MMF_SHARD_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+int mmf_shard_unique_id(void* id_out);
+int mmf_shard_init(mmf_handle* h, int rank, int world, const void* unique_id);
+int mmf_shard_finalize(mmf_handle* h);
+int mmf_shard_info(const mmf_handle* h, int* rank, int* world, int* nccl_version);
+/* mmf_vault_search over ALL shards: local search (top_k candidates per query, global row ids) + all-gather +
+ * merge, asynchronous on `stream` (the collective runs on that stream too); every rank must call it with the
+ * same queries, n_queries and top_k.  Outputs as mmf_vault_search, the same on every rank. */
+int mmf_vault_search_sharded(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
+                             int algo, float* out_scores, int64_t* out_rows, float* out_discrepancy,
+                             mmf_stream_t stream);
+/* The collective alone, for callers that time or overlap the phases themselves (bench.py does): n_keys packed
+ * candidates of this rank (mmf_vault_search_candidates) -> out_gathered (world, n_keys) in rank order.
+ * Then mmf_topk_merge(h, out_gathered, world, n_queries, k_in, ...). */
+int mmf_shard_all_gather(mmf_handle* h, const uint64_t* local_packed, int64_t n_keys, uint64_t* out_gathered,
+                         mmf_stream_t stream);
 
 /* ---- Candidate exchange over NVLink peer memory (row-sharded search) ------------------
  * Alternative to "mmf_vault_search_candidates + NCCL all-gather + mmf_topk_merge": every rank stores its
@@ -199,8 +226,9 @@ int mmf_mma_hist_bound(const float* scores, int64_t n, int top_k, float* out_bou
  * re-scored exactly.  Host-only. */
 double mmf_mma_screen_eps(void);
 
-/* Number of kernel launches this handle has issued (for bench.py's gpu_launches). */
+/* Number of kernel launches this handle has issued (for bench.py's gpu_launches), and of library collectives. */
 int64_t mmf_launch_count(const mmf_handle* h);
+int64_t mmf_collective_count(const mmf_handle* h);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-OK, ERR_BAD_ARG, ERR_CUDA, ERR_NOT_LOADED, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_NOT_LOADED, ERR_NO_DEVICE, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6, -7
+SHARD_ID_BYTES = 128
 F32, F16, BF16, F64 = 0, 1, 2, 3
 VAULT_FP32, VAULT_BF16 = 0, 1
 ALGO_AUTO, ALGO_STREAM, ALGO_MMA = 0, 1, 2
@@ -30,6 +31,12 @@ SIGNATURES = {
     "mmf_vault_search_host": (_i, [_p, _p, _l, _i, _d, _i, _p, _p, _p]),
     "mmf_vault_search_candidates": (_i, [_p, _p, _l, _i, _i, _p, _p]),
     "mmf_topk_merge": (_i, [_p, _p, _i, _l, _i, _i, _d, _p, _p, _p, _p]),
+    "mmf_shard_unique_id": (_i, [_p]),
+    "mmf_shard_init": (_i, [_p, _i, _i, _p]),
+    "mmf_shard_finalize": (_i, [_p]),
+    "mmf_shard_info": (_i, [_p, C.POINTER(_i), C.POINTER(_i), C.POINTER(_i)]),
+    "mmf_vault_search_sharded": (_i, [_p, _p, _l, _i, _d, _i, _p, _p, _p, _p]),
+    "mmf_shard_all_gather": (_i, [_p, _p, _l, _p, _p]),
     "mmf_exchange_layout": (_i, [_i, _l, _i, C.POINTER(_l), C.POINTER(_l)]),
     "mmf_exchange_attach": (_i, [_p, _i, _i, C.POINTER(C.c_uint64), _l]),
     "mmf_exchange_detach": (_i, [_p]),
@@ -44,6 +51,7 @@ SIGNATURES = {
     "mmf_mma_hist_bound": (_i, [_p, _l, _i, C.POINTER(C.c_float)]),
     "mmf_mma_screen_eps": (_d, []),
     "mmf_launch_count": (_l, [_p]),
+    "mmf_collective_count": (_l, [_p]),
 }
 
 

@@ -1,8 +1,10 @@
 // C-ABI glue: handle lifetime, error strings, scratch, search dispatch, host-buffer entry.
 #include "common.cuh"
 
+#include <cctype>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <new>
@@ -14,6 +16,7 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
 int mmf_mma_supported(const mmf_handle* h, int64_t n_queries, int top_k);
 void mmf_mma_destroy(mmf_handle* h);
 extern "C" int mmf_exchange_detach(mmf_handle* h);
+extern "C" int mmf_shard_finalize(mmf_handle* h);
 int mmf_fill_empty(mmf_handle* h, int64_t n_queries, int top_k, float* out_scores, int64_t* out_rows,
                    uint64_t* out_packed, float* out_disc, cudaStream_t st);
 
@@ -30,30 +33,56 @@ int mmf_set_error(mmf_handle* h, int status, const char* fmt, ...) {
 }
 
 int mmf_ensure_scratch(mmf_handle* h, size_t bytes, cudaStream_t stream) {
-  if (bytes <= h->scratch_bytes) return MMF_OK;
-  // growth is rare (first call / larger batch): drain the device, then reallocate
+  const int a = h->scratch_sel;
+  if (bytes <= h->scratch_arena_bytes[a]) return MMF_OK;
+  // growth is rare (first call / larger batch).  It frees memory that earlier calls may still be using, so it
+  // waits for the device (cudaFree does anyway) -- which a stream capture does not allow: size the scratch by
+  // running the step once before capturing it.
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+    return mmf_set_error(h, MMF_ERR_UNSUPPORTED, "scratch must grow to %zu bytes during a stream capture: run the step once before capturing", bytes);
+  cudaGetLastError();
   MMF_CUDA_OK(h, cudaDeviceSynchronize());
-  if (h->scratch) MMF_CUDA_OK(h, cudaFree(h->scratch));
-  h->scratch = nullptr;
-  h->scratch_bytes = 0;
+  if (h->scratch_arena[a]) MMF_CUDA_OK(h, cudaFree(h->scratch_arena[a]));
+  h->scratch_arena[a] = nullptr;
+  h->scratch_arena_bytes[a] = 0;
   const size_t want = std::max(bytes + bytes / 4, (size_t)1 << 22);
-  if (cudaMalloc(&h->scratch, want) != cudaSuccess) {
+  if (cudaMalloc(&h->scratch_arena[a], want) != cudaSuccess) {
     cudaGetLastError();
     return mmf_set_error(h, MMF_ERR_NOMEM, "cannot allocate %zu bytes of scratch", want);
   }
-  h->scratch_bytes = want;
-  MMF_CUDA_OK(h, cudaMemsetAsync(h->scratch, 0, 65536, stream));   // arrival counters start at 0
+  h->scratch_arena_bytes[a] = want;
+  MMF_CUDA_OK(h, cudaMemsetAsync(h->scratch_arena[a], 0, 65536, stream));   // arrival counters start at 0
   return MMF_OK;
 }
 
-static int ensure_pinned(mmf_handle* h, size_t bytes) {
-  if (bytes <= h->pinned_bytes) return MMF_OK;
-  if (h->pinned) MMF_CUDA_OK(h, cudaFreeHost(h->pinned));
-  h->pinned = nullptr;
-  h->pinned_bytes = 0;
-  const size_t want = std::max(bytes, (size_t)1 << 20);
-  MMF_CUDA_OK(h, cudaMallocHost(&h->pinned, want));
-  h->pinned_bytes = want;
+// device I/O + pinned staging of one host-entry slot; growth waits for the slot's previous user (it is not busy:
+// collected) and for nothing else
+static int ensure_slot(mmf_handle* h, mmf_host_slot& sl, size_t io_bytes, size_t pinned_bytes) {
+  if (!sl.ev_in) {
+    MMF_CUDA_OK(h, cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+    MMF_CUDA_OK(h, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+    MMF_CUDA_OK(h, cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+  }
+  if (pinned_bytes > sl.pinned_bytes) {
+    if (sl.pinned) MMF_CUDA_OK(h, cudaFreeHost(sl.pinned));
+    sl.pinned = nullptr;
+    sl.pinned_bytes = 0;
+    const size_t want = std::max(pinned_bytes + pinned_bytes / 4, (size_t)1 << 20);
+    MMF_CUDA_OK(h, cudaMallocHost(&sl.pinned, want));
+    sl.pinned_bytes = want;
+  }
+  if (io_bytes > sl.io_bytes) {
+    if (sl.io) MMF_CUDA_OK(h, cudaFree(sl.io));
+    sl.io = nullptr;
+    sl.io_bytes = 0;
+    const size_t want = io_bytes + io_bytes / 4;
+    if (cudaMalloc(&sl.io, want) != cudaSuccess) {
+      cudaGetLastError();
+      return mmf_set_error(h, MMF_ERR_NOMEM, "cannot allocate %zu bytes of I/O buffer", want);
+    }
+    sl.io_bytes = want;
+  }
   return MMF_OK;
 }
 
@@ -69,6 +98,7 @@ extern "C" const char* mmf_status_string(int status) {
     case MMF_ERR_NO_DEVICE: return "no CUDA device";
     case MMF_ERR_UNSUPPORTED: return "unsupported";
     case MMF_ERR_NOMEM: return "out of device memory";
+    case MMF_ERR_NCCL: return "NCCL error";
   }
   return "unknown status";
 }
@@ -87,11 +117,47 @@ extern "C" int mmf_create(int device_ordinal, mmf_handle** out) {
   h->device = device_ordinal;
   h->sm_count = prop.multiProcessorCount;
   if (cudaSetDevice(device_ordinal) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete h;
     return MMF_ERR_CUDA;
   }
+  // the only place the environment is read: MMF_OPT_SCREEN, MMF_OPT_FUSED_PUSH, MMF_OPT_DEBUG, MMF_OPT_FORCE_CG,
+  // MMF_OPT_FLAT_SCHEDULE (same names as mmf_set_option, upper case)
+  for (const char* name : {"screen", "fused_push", "debug", "force_cg", "flat_schedule"}) {
+    char env[64] = "MMF_OPT_";
+    size_t n = strlen(env);
+    for (const char* c = name; *c && n + 1 < sizeof env; ++c) env[n++] = (char)toupper((unsigned char)*c);
+    env[n] = 0;
+    const char* v = getenv(env);
+    if (v && *v) mmf_set_option(h, name, atoi(v));
+  }
   *out = h;
+  return MMF_OK;
+}
+
+extern "C" int mmf_set_option(mmf_handle* h, const char* name, int value) {
+  if (!h || !name) return MMF_ERR_BAD_ARG;
+  mmf_options& o = h->opt;
+  if (!strcmp(name, "screen")) o.screen = value != 0;
+  else if (!strcmp(name, "fused_push")) o.fused_push = value != 0;
+  else if (!strcmp(name, "debug")) o.debug = value;
+  else if (!strcmp(name, "force_cg")) o.force_cg = (value == 1 || value == 2) ? value : 0;
+  else if (!strcmp(name, "flat_schedule")) o.flat_schedule = value != 0;
+  else return mmf_set_error(h, MMF_ERR_BAD_ARG, "set_option: unknown option '%s'", name);
+  return MMF_OK;
+}
+
+extern "C" int mmf_get_option(const mmf_handle* h, const char* name, int* value) {
+  if (!h || !name || !value) return MMF_ERR_BAD_ARG;
+  const mmf_options& o = h->opt;
+  if (!strcmp(name, "screen")) *value = o.screen;
+  else if (!strcmp(name, "fused_push")) *value = o.fused_push;
+  else if (!strcmp(name, "debug")) *value = o.debug;
+  else if (!strcmp(name, "force_cg")) *value = o.force_cg;
+  else if (!strcmp(name, "flat_schedule")) *value = o.flat_schedule;
+  else return MMF_ERR_BAD_ARG;
   return MMF_OK;
 }
 
@@ -99,21 +165,29 @@ extern "C" int mmf_destroy(mmf_handle* h) {
   if (!h) return MMF_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  mmf_shard_finalize(h);
   mmf_exchange_detach(h);
   mmf_mma_destroy(h);
   if (h->vault) cudaFree(h->vault);
   if (h->fusion_params) cudaFree(h->fusion_params);
   if (h->vault_nan_rows_dev) cudaFree(h->vault_nan_rows_dev);
-  if (h->scratch) cudaFree(h->scratch);
-  if (h->pinned) cudaFreeHost(h->pinned);
-  if (h->io) cudaFree(h->io);
-  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int a = 0; a < 2; ++a)
+    if (h->scratch_arena[a]) cudaFree(h->scratch_arena[a]);
+  for (mmf_host_slot& sl : h->slot) {
+    if (sl.pinned) cudaFreeHost(sl.pinned);
+    if (sl.io) cudaFree(sl.io);
+    for (cudaEvent_t e : {sl.ev_in, sl.ev_done, sl.ev_out})
+      if (e) cudaEventDestroy(e);
+  }
+  for (cudaStream_t st : {h->own_stream, h->h2d_stream, h->d2h_stream})
+    if (st) cudaStreamDestroy(st);
   delete h;
   return MMF_OK;
 }
 
 extern "C" const char* mmf_last_error(const mmf_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
 extern "C" int64_t mmf_launch_count(const mmf_handle* h) { return h ? h->launches : 0; }
+extern "C" int64_t mmf_collective_count(const mmf_handle* h) { return h ? h->collectives : 0; }
 
 static int search_dispatch(mmf_handle* h, const float* queries, int64_t n_queries, int top_k, double threshold,
                            int algo, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,

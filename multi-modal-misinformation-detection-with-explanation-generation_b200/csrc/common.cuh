@@ -79,11 +79,33 @@ struct mmf_push_ctx {
 };
 
 // ---- handle ----------------------------------------------------------------------------
+// Switches of a handle.  Read ONCE from the environment at mmf_create (MMF_OPT_<NAME>, upper case) and settable
+// with mmf_set_option; never consulted through getenv on the search path.
+struct mmf_options {
+  int screen = 1;          // fp32-exact vaults, top_k <= 16: screened search (1) or the 3-pass kernel (0, A/B + triage)
+  int fused_push = 1;      // peer-memory exchange: the search's merge tail pushes the winners itself where it can
+  int debug = 0;           // tcgen05 search triage bits: 1 skip the filter, 2 skip the vault TMA, 4 skip the MMA waits, 8 print clocks
+  int force_cg = 0;        // tcgen05 search: force 1 or 2 CTAs per MMA (0 = automatic)
+  int flat_schedule = 0;   // tcgen05 search: plain flattened schedule instead of the L2-aware one
+};
+
+// One in-flight batch of the host-buffer entry points (api.cu): device I/O buffers, pinned staging for the results
+struct mmf_host_slot {
+  void* io = nullptr;      size_t io_bytes = 0;        // device: inputs, then one contiguous block of outputs
+  void* pinned = nullptr;  size_t pinned_bytes = 0;    // host mirror of the output block
+  cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+  bool busy = false;
+  int64_t n = 0;
+  int top_k = 0;
+};
+
 struct mmf_handle {
   int device = -1;
   int sm_count = 148;
   std::string last_error;
   int64_t launches = 0;
+  int64_t collectives = 0;
+  mmf_options opt;
   // vault shard
   void* vault = nullptr;            // FP32 mode: [n][2][512] fp16 (hi row, lo row); BF16: [n][512] bf16
   bool vault_loaded = false;
@@ -96,16 +118,19 @@ struct mmf_handle {
   // fusion judge
   float* fusion_params = nullptr;   // device, MMF_FUSION_PARAMS floats, re-laid out (see fusion.cu)
   bool fusion_loaded = false;
-  // scratch
-  void* scratch = nullptr;
-  size_t scratch_bytes = 0;
-  void* pinned = nullptr;          // host staging for the *_host entry points
-  size_t pinned_bytes = 0;
-  void* io = nullptr;              // device mirror of the staging buffer
-  size_t io_bytes = 0;
-  cudaStream_t own_stream = nullptr;
+  // scratch: arena 0 serves the asynchronous entry points (caller's stream), arena 1 the *_host / submit entry
+  // points (the handle's own stream), so that the two families never share counters or candidate lists
+  void* scratch_arena[2] = {nullptr, nullptr};
+  size_t scratch_arena_bytes[2] = {0, 0};
+  int scratch_sel = 0;
+  void* scratch() const { return scratch_arena[scratch_sel]; }
+  mmf_host_slot slot[2];
+  cudaStream_t own_stream = nullptr;       // compute of the host-buffer entry points
+  cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
   // TMA descriptors for the tcgen05 path live in vault_mma.cu's state
   void* mma_state = nullptr;
+  // row-sharded search with the library's own NCCL communicator (shard.cu), null until mmf_shard_init
+  void* shard_state = nullptr;
   // peer-memory candidate exchange (exchange.cu), null until mmf_exchange_attach
   void* xchg_state = nullptr;
   const mmf_push_ctx* push_ctx = nullptr;   // non-null only inside mmf_vault_search_exchange (fused push requested)

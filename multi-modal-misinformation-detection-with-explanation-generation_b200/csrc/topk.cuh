@@ -342,7 +342,12 @@ __device__ __forceinline__ u32 stage_candidates(const CandidateLists& src, Selec
     }
   }
   __syncthreads();
-  return sm.n_staged;
+  const u32 n = sm.n_staged;
+  // every thread must have READ the count before anyone goes on: the caller may enter block_select_topk next, whose
+  // first statement lets thread 0 reset sm.n_staged (a warp that read 0 here took a different branch than the rest:
+  // the lost-candidates bug of the first fast tails, seen whenever more than RANK_SELECT_MAX keys were staged)
+  __syncthreads();
+  return n;
 }
 
 // Step 3: sm.win[0..top_k) (sorted descending, 0 = empty) -> the output arrays, as block_select_topk writes them.

@@ -1451,7 +1451,7 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                             : screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
-  char* sc = (char*)h->scratch;
+  char* sc = (char*)h->scratch();
   void* planes = sc + off_q;
   p.cand_cnt = (int*)(sc + off_cnt);
   p.cand = (u64*)(sc + off_cand);

@@ -420,7 +420,7 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   const size_t total = screen ? off_tau2 + align_up((size_t)Q * 4 + 256, 256) : off_keys + (size_t)gx * Q * top_k * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
-  char* s = (char*)h->scratch;
+  char* s = (char*)h->scratch();
   float* qn = (float*)(s + off_qn);
   u32* g_tau = (u32*)(s + off_tau);
 
