@@ -12,7 +12,10 @@
  *  - unless a name ends in _host, data pointers are DEVICE pointers on the handle's
  *    device (torch.Tensor.data_ptr() passes zero-copy) and the call is ASYNCHRONOUS on
  *    the cudaStream_t given as `stream` (torch.cuda.current_stream().cuda_stream); no
- *    hidden synchronisation.  *_host calls take host pointers, include the H2D / D2H
+ *    hidden synchronisation, with one exception: when a call needs more scratch than any
+ *    earlier one (first call, larger batch) the scratch is re-allocated, which waits for
+ *    the device -- and is refused during a stream capture: run a step once before
+ *    capturing it.  *_host calls take host pointers, include the H2D / D2H
  *    copies and return after the result is in host memory;
  *  - a handle is not thread-safe: one handle per (process, device), calls serialised by
  *    the caller (the reference is single-threaded and synchronous);
@@ -198,8 +201,8 @@ int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modalit
 
 /* The whole path for a batch with HOST buffers in and out (the end-to-end call): H2D of the embeddings,
  * caption/image cosine, vault search (zero discrepancy / no matches when no vault is loaded, misinfo_forensics.py:
- * 422-428), score assembly with the skipped-modality zeros of :794-809, fusion judge / fallback verdict, one D2H,
- * one stream synchronisation; returns when the results are in host memory.  Pinned host buffers make the copies
+ * 422-428), score assembly with the skipped-modality zeros of :794-809 + fusion judge / fallback verdict, one D2H,
+ * one synchronisation; returns when the results are in host memory.  Pinned host buffers make the copies
  * asynchronous DMA.  text/image: (n,512) fp32; head: (n,3) fp32 = [ai, misinfo, deepfake]; modality: (n) uint8
  * (bit0 text, bit1 visual) or NULL = both.  Outputs (any but out_probs may be NULL): clip_similarity (n),
  * vault_discrepancy (n), vault_scores (n,top_k), vault_rows (n,top_k) int64, scores5 (n,5) = the fusion inputs,
@@ -209,6 +212,26 @@ int mmf_score_batch_host(mmf_handle* h, const float* text_host, const float* ima
                          float* out_clip_similarity, float* out_vault_discrepancy, float* out_vault_scores,
                          int64_t* out_vault_rows, float* out_scores5, float* out_probs, int32_t* out_verdict,
                          float* out_confidence);
+/* The same call split in two, with two slots (0, 1): submit enqueues H2D + kernels + D2H on the handle's own
+ * streams and returns at once; collect waits for that slot and copies the results out.  A caller that submits batch
+ * i+1 before collecting batch i overlaps the copies of one with the kernels of the other (throughput serving).
+ * The input buffers of a slot must stay valid until it is collected; mmf_score_batch_host == submit + collect on
+ * slot 0.  The host entry points use their own streams and their own scratch, so they may be mixed with the
+ * asynchronous entry points; do not call mmf_fusion_load / mmf_vault_load while a slot is pending. */
+int mmf_score_batch_submit(mmf_handle* h, int slot, const float* text_host, const float* image_host,
+                           const float* head_host, const uint8_t* modality_host, int64_t n, int top_k,
+                           double threshold, int algo);
+int mmf_score_batch_collect(mmf_handle* h, int slot, float* out_clip_similarity, float* out_vault_discrepancy,
+                            float* out_vault_scores, int64_t* out_vault_rows, float* out_scores5, float* out_probs,
+                            int32_t* out_verdict, float* out_confidence);
+
+/* Switches of a handle (A/B and triage; production needs none).  Read once from the environment at mmf_create
+ * (MMF_OPT_<NAME>), never on the search path.  Names: "screen" (fp32-exact vaults, top_k <= 16: 1 = screened
+ * search, default; 0 = 3-pass kernel), "fused_push" (peer-memory exchange: the search pushes its winners itself,
+ * default 1), "debug" (tcgen05 search triage bits), "force_cg" (1 / 2 CTAs per MMA, 0 = automatic),
+ * "flat_schedule", "epi_parity". */
+int mmf_set_option(mmf_handle* h, const char* name, int value);
+int mmf_get_option(const mmf_handle* h, const char* name, int* value);
 
 /* Host-only self check of the tcgen05 search's work decomposition for a (n_queries, n_rows) problem on a
  * device with sm_count SMs: MMF_OK iff every (query-tile group, vault tile) unit is scheduled exactly once,

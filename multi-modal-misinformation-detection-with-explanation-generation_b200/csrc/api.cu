@@ -103,6 +103,8 @@ extern "C" const char* mmf_status_string(int status) {
   return "unknown status";
 }
 
+extern "C" int mmf_set_option(mmf_handle* h, const char* name, int value);
+
 extern "C" int mmf_create(int device_ordinal, mmf_handle** out) {
   if (!out) return MMF_ERR_BAD_ARG;
   *out = nullptr;
@@ -125,7 +127,7 @@ extern "C" int mmf_create(int device_ordinal, mmf_handle** out) {
   }
   // the only place the environment is read: MMF_OPT_SCREEN, MMF_OPT_FUSED_PUSH, MMF_OPT_DEBUG, MMF_OPT_FORCE_CG,
   // MMF_OPT_FLAT_SCHEDULE (same names as mmf_set_option, upper case)
-  for (const char* name : {"screen", "fused_push", "debug", "force_cg", "flat_schedule"}) {
+  for (const char* name : {"screen", "fused_push", "debug", "force_cg", "flat_schedule", "epi_parity"}) {
     char env[64] = "MMF_OPT_";
     size_t n = strlen(env);
     for (const char* c = name; *c && n + 1 < sizeof env; ++c) env[n++] = (char)toupper((unsigned char)*c);
@@ -145,6 +147,7 @@ extern "C" int mmf_set_option(mmf_handle* h, const char* name, int value) {
   else if (!strcmp(name, "debug")) o.debug = value;
   else if (!strcmp(name, "force_cg")) o.force_cg = (value == 1 || value == 2) ? value : 0;
   else if (!strcmp(name, "flat_schedule")) o.flat_schedule = value != 0;
+  else if (!strcmp(name, "epi_parity")) o.epi_parity = value < 0 ? -1 : (value != 0);
   else return mmf_set_error(h, MMF_ERR_BAD_ARG, "set_option: unknown option '%s'", name);
   return MMF_OK;
 }
@@ -157,6 +160,7 @@ extern "C" int mmf_get_option(const mmf_handle* h, const char* name, int* value)
   else if (!strcmp(name, "debug")) *value = o.debug;
   else if (!strcmp(name, "force_cg")) *value = o.force_cg;
   else if (!strcmp(name, "flat_schedule")) *value = o.flat_schedule;
+  else if (!strcmp(name, "epi_parity")) *value = o.epi_parity;
   else return MMF_ERR_BAD_ARG;
   return MMF_OK;
 }
@@ -249,6 +253,14 @@ extern "C" int mmf_vault_search_candidates(mmf_handle* h, const float* queries, 
                          (cudaStream_t)stream, "vault_search_candidates");
 }
 
+// RAII: the host-buffer entry points run on the handle's own streams with their own scratch arena (arena 1), so
+// that they never share counters or candidate lists with an asynchronous search in flight on a caller's stream
+struct HostArena {
+  mmf_handle* h;
+  explicit HostArena(mmf_handle* hh) : h(hh) { h->scratch_sel = 1; }
+  ~HostArena() { h->scratch_sel = 0; }
+};
+
 extern "C" int mmf_vault_search_host(mmf_handle* h, const float* queries_host, int64_t n_queries, int top_k,
                                      double threshold, int algo, float* out_scores_host, int64_t* out_rows_host,
                                      float* out_discrepancy_host) {
@@ -258,66 +270,137 @@ extern "C" int mmf_vault_search_host(mmf_handle* h, const float* queries_host, i
     return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_host: bad argument");
   if (!h->vault_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "vault_search_host: no vault loaded");
   if (n_queries == 0) return MMF_OK;
+  mmf_host_slot& sl = h->slot[0];
+  if (sl.busy) return mmf_set_error(h, MMF_ERR_BAD_ARG, "vault_search_host: a submitted batch is pending in slot 0 (collect it first)");
   MMF_CUDA_OK(h, cudaSetDevice(h->device));
   cudaStream_t st = h->own_stream;
-  // pinned staging: [queries | scores | rows | disc]; device I/O buffers mirror it
+  // device: [queries | scores | rows | disc]; the pinned staging mirrors the outputs
   auto al = [](size_t x) { return (x + 255) / 256 * 256; };
   const size_t bq = al((size_t)n_queries * MMF_DIM * 4), bs = al((size_t)n_queries * top_k * 4);
   const size_t br = al((size_t)n_queries * top_k * 8), bd = al((size_t)n_queries * 4);
-  const size_t total = bq + bs + br + bd;
-  int rc = ensure_pinned(h, total);
+  int rc = ensure_slot(h, sl, bq + bs + br + bd, bs + br + bd);
   if (rc != MMF_OK) return rc;
-  if (total > h->io_bytes) {
-    if (h->io) MMF_CUDA_OK(h, cudaFree(h->io));
-    h->io = nullptr;
-    h->io_bytes = 0;
-    MMF_CUDA_OK(h, cudaMalloc(&h->io, total));
-    h->io_bytes = total;
-  }
-  char* hp = (char*)h->pinned;
-  char* dp = (char*)h->io;
-  memcpy(hp, queries_host, (size_t)n_queries * MMF_DIM * 4);
-  MMF_CUDA_OK(h, cudaMemcpyAsync(dp, hp, bq, cudaMemcpyHostToDevice, st));
+  HostArena arena(h);
+  char* hp = (char*)sl.pinned;
+  char* dp = (char*)sl.io;
+  MMF_CUDA_OK(h, cudaMemcpyAsync(dp, queries_host, (size_t)n_queries * MMF_DIM * 4, cudaMemcpyHostToDevice, st));
   float* d_scores = (float*)(dp + bq);
   int64_t* d_rows = (int64_t*)(dp + bq + bs);
   float* d_disc = (float*)(dp + bq + bs + br);
   rc = search_dispatch(h, (const float*)dp, n_queries, top_k, threshold, algo, d_scores, d_rows, nullptr, d_disc, st,
                        "vault_search_host");
   if (rc != MMF_OK) return rc;
-  MMF_CUDA_OK(h, cudaMemcpyAsync(hp + bq, dp + bq, bs + br + bd, cudaMemcpyDeviceToHost, st));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(hp, dp + bq, bs + br + bd, cudaMemcpyDeviceToHost, st));
   MMF_CUDA_OK(h, cudaStreamSynchronize(st));
-  memcpy(out_scores_host, hp + bq, (size_t)n_queries * top_k * 4);
-  memcpy(out_rows_host, hp + bq + bs, (size_t)n_queries * top_k * 8);
-  if (out_discrepancy_host) memcpy(out_discrepancy_host, hp + bq + bs + br, (size_t)n_queries * 4);
+  memcpy(out_scores_host, hp, (size_t)n_queries * top_k * 4);
+  memcpy(out_rows_host, hp + bs, (size_t)n_queries * top_k * 8);
+  if (out_discrepancy_host) memcpy(out_discrepancy_host, hp + bs + br, (size_t)n_queries * 4);
   return MMF_OK;
 }
 
 // ---- batched analyze downstream of the encoders, HOST buffers in and out ---------------------------------
-// The whole hot path for a batch in one call: H2D of the embeddings, caption/image cosine (K1), vault search
-// (K2 / K3), score assembly with the modality rules of misinfo_forensics.py:794-809, fusion judge / fallback
-// verdict (K5), ONE D2H of all results, ONE stream synchronisation.  Same results as mmf_b200.score_batch
-// (pipeline.py), which issues the same kernels from Python with one torch op and one .cpu() sync per tensor.
-namespace mmf {
-// x[i] = [ai, misinfo, deepfake, clip_sim, vault_disc] with the skipped modalities zeroed; sim / disc masked in place
-__global__ void __launch_bounds__(256) assemble_scores_kernel(const float* __restrict__ head, const unsigned char* __restrict__ mod_in,
-                                                              long long n, float* __restrict__ sim, float* __restrict__ disc,
-                                                              float* __restrict__ x, unsigned char* __restrict__ mod_out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int mod = mod_in ? mod_in[i] : 3;
-  const bool has_text = mod & 1, has_vis = mod & 2;
-  const float s = (has_text && has_vis) ? sim[i] : 0.f;      // analyze() skips the steps whose modality is missing
-  const float d = has_vis ? disc[i] : 0.f;
-  sim[i] = s;
-  disc[i] = d;
-  x[i * 5 + 0] = has_text ? head[i * 3 + 0] : 0.f;
-  x[i * 5 + 1] = has_text ? head[i * 3 + 1] : 0.f;
-  x[i * 5 + 2] = has_vis ? head[i * 3 + 2] : 0.f;
-  x[i * 5 + 3] = s;
-  x[i * 5 + 4] = d;
-  mod_out[i] = (unsigned char)mod;
+// The whole hot path for a batch: H2D of the embeddings, caption/image cosine (K1), vault search (K2 / K3), score
+// assembly with the modality rules of misinfo_forensics.py:794-809 + fusion judge / fallback verdict (K5, one
+// launch), ONE D2H of all results.  Two slots and three streams (H2D, compute, D2H) let a caller keep two batches in
+// flight: the copies of one overlap the kernels of the other (mmf_score_batch_submit / _collect); the synchronous
+// mmf_score_batch_host is submit + collect on slot 0.
+int mmf_assemble_verdict(mmf_handle* h, const float* head, const uint8_t* modality_in, int64_t n, float* sim, float* disc,
+                         float* x, float* out_probs, int32_t* out_verdict, float* out_conf, cudaStream_t st);
+
+namespace {
+struct BatchLayout {       // byte offsets inside a slot's device buffer: inputs, then the output block
+  size_t text, img, head, mod, in_bytes;
+  size_t o_sim, o_disc, o_vs, o_vr, o_x, o_probs, o_verdict, o_conf, out_bytes;
+  BatchLayout(int64_t n, int top_k) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t b_emb = al((size_t)n * MMF_DIM * 4);
+    text = 0; img = b_emb; head = 2 * b_emb; mod = head + al((size_t)n * 3 * 4); in_bytes = mod + al((size_t)n);
+    o_sim = 0; o_disc = o_sim + al((size_t)n * 4); o_vs = o_disc + al((size_t)n * 4);
+    o_vr = o_vs + al((size_t)n * top_k * 4); o_x = o_vr + al((size_t)n * top_k * 8);
+    o_probs = o_x + al((size_t)n * 5 * 4); o_verdict = o_probs + al((size_t)n * 2 * 4);
+    o_conf = o_verdict + al((size_t)n * 4); out_bytes = o_conf + al((size_t)n * 4);
+  }
+};
+}  // namespace
+
+extern "C" int mmf_score_batch_submit(mmf_handle* h, int slot, const float* text_host, const float* image_host,
+                                      const float* head_host, const uint8_t* modality_host, int64_t n, int top_k,
+                                      double threshold, int algo) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (slot < 0 || slot > 1 || n < 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K || (n > 0 && (!text_host || !image_host || !head_host)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_submit: bad argument (slot=%d n=%lld top_k=%d)", slot, (long long)n, top_k);
+  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "score_batch_submit: fusion weights not loaded");
+  mmf_host_slot& sl = h->slot[slot];
+  if (sl.busy) return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_submit: slot %d has not been collected", slot);
+  sl.n = n;
+  sl.top_k = top_k;
+  if (n == 0) { sl.busy = true; return MMF_OK; }
+  MMF_CUDA_OK(h, cudaSetDevice(h->device));
+  const BatchLayout L(n, top_k);
+  int rc = ensure_slot(h, sl, L.in_bytes + L.out_bytes, L.out_bytes);
+  if (rc != MMF_OK) return rc;                       // (every error path leaves the slot free)
+  HostArena arena(h);
+  char* dp = (char*)sl.io;
+  char* dout = dp + L.in_bytes;
+  float* d_text = (float*)(dp + L.text);
+  float* d_img = (float*)(dp + L.img);
+  float* d_head = (float*)(dp + L.head);
+  uint8_t* d_mod = (uint8_t*)(dp + L.mod);
+  // H2D straight from the caller's buffers (asynchronous DMA when they are pinned; they must stay valid until the
+  // batch is collected).  The image embeddings go first: the search needs nothing else.
+  cudaStream_t up = h->h2d_stream, st = h->own_stream, down = h->d2h_stream;
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_img, image_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, up));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_text, text_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, up));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(d_head, head_host, (size_t)n * 3 * 4, cudaMemcpyHostToDevice, up));
+  if (modality_host) MMF_CUDA_OK(h, cudaMemcpyAsync(d_mod, modality_host, (size_t)n, cudaMemcpyHostToDevice, up));
+  MMF_CUDA_OK(h, cudaEventRecord(sl.ev_in, up));
+  MMF_CUDA_OK(h, cudaStreamWaitEvent(st, sl.ev_in, 0));
+  float* d_sim = (float*)(dout + L.o_sim);
+  float* d_disc = (float*)(dout + L.o_disc);
+  rc = mmf_cosine_pairs(h, d_text, d_img, n, MMF_DIM, 0.0, d_sim, nullptr, st);
+  if (rc != MMF_OK) return rc;
+  if (h->vault_loaded) {
+    rc = search_dispatch(h, d_img, n, top_k, threshold, algo, (float*)(dout + L.o_vs), (int64_t*)(dout + L.o_vr), nullptr,
+                         d_disc, st, "score_batch_submit");
+  } else {      // reference: vault_loaded == False -> zero discrepancy, no matches (misinfo_forensics.py:422-428)
+    rc = mmf_fill_empty(h, n, top_k, (float*)(dout + L.o_vs), (int64_t*)(dout + L.o_vr), nullptr, d_disc, st);
+  }
+  if (rc != MMF_OK) return rc;
+  rc = mmf_assemble_verdict(h, d_head, modality_host ? d_mod : nullptr, n, d_sim, d_disc, (float*)(dout + L.o_x),
+                            (float*)(dout + L.o_probs), (int32_t*)(dout + L.o_verdict), (float*)(dout + L.o_conf), st);
+  if (rc != MMF_OK) return rc;
+  MMF_CUDA_OK(h, cudaEventRecord(sl.ev_done, st));
+  MMF_CUDA_OK(h, cudaStreamWaitEvent(down, sl.ev_done, 0));
+  MMF_CUDA_OK(h, cudaMemcpyAsync(sl.pinned, dout, L.out_bytes, cudaMemcpyDeviceToHost, down));
+  MMF_CUDA_OK(h, cudaEventRecord(sl.ev_out, down));
+  sl.busy = true;
+  return MMF_OK;
 }
-}  // namespace mmf
+
+extern "C" int mmf_score_batch_collect(mmf_handle* h, int slot, float* out_clip_similarity, float* out_vault_discrepancy,
+                                       float* out_vault_scores, int64_t* out_vault_rows, float* out_scores5,
+                                       float* out_probs, int32_t* out_verdict, float* out_confidence) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (slot < 0 || slot > 1) return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_collect: bad slot %d", slot);
+  mmf_host_slot& sl = h->slot[slot];
+  if (!sl.busy) return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_collect: nothing submitted in slot %d", slot);
+  sl.busy = false;
+  const int64_t n = sl.n;
+  if (n == 0) return MMF_OK;
+  if (!out_probs) return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_collect: null out_probs");
+  MMF_CUDA_OK(h, cudaEventSynchronize(sl.ev_out));
+  const BatchLayout L(n, sl.top_k);
+  const char* hp = (const char*)sl.pinned;
+  if (out_clip_similarity) memcpy(out_clip_similarity, hp + L.o_sim, (size_t)n * 4);
+  if (out_vault_discrepancy) memcpy(out_vault_discrepancy, hp + L.o_disc, (size_t)n * 4);
+  if (out_vault_scores) memcpy(out_vault_scores, hp + L.o_vs, (size_t)n * sl.top_k * 4);
+  if (out_vault_rows) memcpy(out_vault_rows, hp + L.o_vr, (size_t)n * sl.top_k * 8);
+  if (out_scores5) memcpy(out_scores5, hp + L.o_x, (size_t)n * 5 * 4);
+  memcpy(out_probs, hp + L.o_probs, (size_t)n * 2 * 4);
+  if (out_verdict) memcpy(out_verdict, hp + L.o_verdict, (size_t)n * 4);
+  if (out_confidence) memcpy(out_confidence, hp + L.o_conf, (size_t)n * 4);
+  return MMF_OK;
+}
 
 extern "C" int mmf_score_batch_host(mmf_handle* h, const float* text_host, const float* image_host, const float* head_host,
                                     const uint8_t* modality_host, int64_t n, int top_k, double threshold, int algo,
@@ -325,77 +408,9 @@ extern "C" int mmf_score_batch_host(mmf_handle* h, const float* text_host, const
                                     int64_t* out_vault_rows, float* out_scores5, float* out_probs, int32_t* out_verdict,
                                     float* out_confidence) {
   if (!h) return MMF_ERR_BAD_ARG;
-  if (n < 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K ||
-      (n > 0 && (!text_host || !image_host || !head_host || !out_probs)))
-    return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_host: bad argument (n=%lld top_k=%d)", (long long)n, top_k);
-  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "score_batch_host: fusion weights not loaded");
-  if (n == 0) return MMF_OK;
-  MMF_CUDA_OK(h, cudaSetDevice(h->device));
-  cudaStream_t st = h->own_stream;
-  auto al = [](size_t x) { return (x + 255) / 256 * 256; };
-  // device buffer: inputs, then ONE contiguous block of outputs (mirrored by the pinned staging buffer)
-  const size_t b_emb = al((size_t)n * MMF_DIM * 4), b_head = al((size_t)n * 3 * 4), b_mod = al((size_t)n);
-  const size_t o_sim = 0, o_disc = o_sim + al((size_t)n * 4), o_vs = o_disc + al((size_t)n * 4);
-  const size_t o_vr = o_vs + al((size_t)n * top_k * 4), o_x = o_vr + al((size_t)n * top_k * 8);
-  const size_t o_probs = o_x + al((size_t)n * 5 * 4), o_verdict = o_probs + al((size_t)n * 2 * 4);
-  const size_t o_conf = o_verdict + al((size_t)n * 4), out_bytes = o_conf + al((size_t)n * 4);
-  const size_t in_bytes = 2 * b_emb + b_head + 2 * b_mod;
-  const size_t total = in_bytes + out_bytes;
-  int rc = ensure_pinned(h, out_bytes);
+  if (n > 0 && !out_probs) return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch_host: bad argument (null out_probs)");
+  const int rc = mmf_score_batch_submit(h, 0, text_host, image_host, head_host, modality_host, n, top_k, threshold, algo);
   if (rc != MMF_OK) return rc;
-  if (total > h->io_bytes) {
-    MMF_CUDA_OK(h, cudaStreamSynchronize(st));
-    if (h->io) MMF_CUDA_OK(h, cudaFree(h->io));
-    h->io = nullptr;
-    h->io_bytes = 0;
-    MMF_CUDA_OK(h, cudaMalloc(&h->io, total));
-    h->io_bytes = total;
-  }
-  char* dp = (char*)h->io;
-  float* d_text = (float*)dp;
-  float* d_img = (float*)(dp + b_emb);
-  float* d_head = (float*)(dp + 2 * b_emb);
-  unsigned char* d_mod_in = (unsigned char*)(dp + 2 * b_emb + b_head);
-  unsigned char* d_mod = d_mod_in + b_mod;
-  char* dout = dp + in_bytes;
-  float* d_sim = (float*)(dout + o_sim);
-  float* d_disc = (float*)(dout + o_disc);
-  float* d_vs = (float*)(dout + o_vs);
-  int64_t* d_vr = (int64_t*)(dout + o_vr);
-  float* d_x = (float*)(dout + o_x);
-  float* d_probs = (float*)(dout + o_probs);
-  int32_t* d_verdict = (int32_t*)(dout + o_verdict);
-  float* d_conf = (float*)(dout + o_conf);
-
-  // straight from the caller's buffers: asynchronous DMA when they are pinned, staged by the driver otherwise
-  MMF_CUDA_OK(h, cudaMemcpyAsync(d_text, text_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, st));
-  MMF_CUDA_OK(h, cudaMemcpyAsync(d_img, image_host, (size_t)n * MMF_DIM * 4, cudaMemcpyHostToDevice, st));
-  MMF_CUDA_OK(h, cudaMemcpyAsync(d_head, head_host, (size_t)n * 3 * 4, cudaMemcpyHostToDevice, st));
-  if (modality_host) MMF_CUDA_OK(h, cudaMemcpyAsync(d_mod_in, modality_host, (size_t)n, cudaMemcpyHostToDevice, st));
-
-  rc = mmf_cosine_pairs(h, d_text, d_img, n, MMF_DIM, 0.0, d_sim, nullptr, st);
-  if (rc != MMF_OK) return rc;
-  if (h->vault_loaded) {
-    rc = search_dispatch(h, d_img, n, top_k, threshold, algo, d_vs, d_vr, nullptr, d_disc, st, "score_batch_host");
-  } else {      // reference: vault_loaded == False -> zero discrepancy, no matches (misinfo_forensics.py:422-428)
-    rc = mmf_fill_empty(h, n, top_k, d_vs, d_vr, nullptr, d_disc, st);
-  }
-  if (rc != MMF_OK) return rc;
-  mmf::assemble_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_head, modality_host ? d_mod_in : nullptr, n, d_sim,
-                                                                          d_disc, d_x, d_mod);
-  MMF_LAUNCH_OK(h);
-  rc = mmf_verdict_batch(h, d_x, d_mod, n, d_probs, d_verdict, d_conf, st);
-  if (rc != MMF_OK) return rc;
-  char* hp = (char*)h->pinned;
-  MMF_CUDA_OK(h, cudaMemcpyAsync(hp, dout, out_bytes, cudaMemcpyDeviceToHost, st));
-  MMF_CUDA_OK(h, cudaStreamSynchronize(st));
-  if (out_clip_similarity) memcpy(out_clip_similarity, hp + o_sim, (size_t)n * 4);
-  if (out_vault_discrepancy) memcpy(out_vault_discrepancy, hp + o_disc, (size_t)n * 4);
-  if (out_vault_scores) memcpy(out_vault_scores, hp + o_vs, (size_t)n * top_k * 4);
-  if (out_vault_rows) memcpy(out_vault_rows, hp + o_vr, (size_t)n * top_k * 8);
-  if (out_scores5) memcpy(out_scores5, hp + o_x, (size_t)n * 5 * 4);
-  memcpy(out_probs, hp + o_probs, (size_t)n * 2 * 4);
-  if (out_verdict) memcpy(out_verdict, hp + o_verdict, (size_t)n * 4);
-  if (out_confidence) memcpy(out_confidence, hp + o_conf, (size_t)n * 4);
-  return MMF_OK;
+  return mmf_score_batch_collect(h, 0, out_clip_similarity, out_vault_discrepancy, out_vault_scores, out_vault_rows,
+                                 out_scores5, out_probs, out_verdict, out_confidence);
 }

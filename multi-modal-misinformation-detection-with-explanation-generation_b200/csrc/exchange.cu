@@ -20,7 +20,8 @@
 // Buffer of one rank (identical layout on all ranks; `bytes_per_rank` as attached):
 //   [0, 1024)            flags: u32 flag[2][MMF_XCHG_MAX_WORLD], flag[parity][src] = epoch of the last exchange
 //                        whose candidates from rank `src` are complete in gather[parity]
-//   [1024, ...)          gather[2][world][n_queries][top_k] u64 (laid out per call; both parities must fit)
+//   [1024, ...)          gather[2][world][n_queries][top_k] u64: parity p starts at 1024 + p * half, half = the
+//                        1 KB-aligned half of the rest of the buffer (fixed at attach; a call must fit one half)
 // Two parities (epoch & 1): a peer may already push exchange e+1 while this rank still merges exchange e.
 // It cannot get to e+2 before this rank has pushed e+1 -- which this rank does after its merge of e, in stream
 // order -- so two buffers are enough and no back-signal is needed.
@@ -31,8 +32,7 @@
 // that is waited for gets to run; B200_PROFILING.md reports Xid 109 for that pattern): the single-device checks
 // (tools/cabi_selftest, tests) enqueue ALL pushes before ANY merge on one stream, so no kernel ever waits.
 //
-// STATUS: compiles for sm_100a; NOT yet run on a multi-GPU box (written after the round's GPU time was spent).
-// Off by default: TruthVault(exchange="p2p") / MMF_EXCHANGE=p2p selects it, the NCCL all-gather stays the default.
+// Selected with TruthVault(exchange="p2p"); the library-owned NCCL all-gather (shard.cu) is the default exchange.
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -215,7 +215,11 @@ extern "C" int mmf_vault_search_push(mmf_handle* h, const float* queries, int64_
   cudaStream_t st = (cudaStream_t)stream;
   int64_t per_parity = 0, need = 0;
   mmf_exchange_layout(x->world, n_queries, k_local, &per_parity, &need);
-  if ((size_t)need > x->bytes_per_rank)
+  // the two parities live at FIXED offsets (the halves of the attached buffer), whatever the batch size of a call:
+  // a peer may already push exchange e+1 while this rank still merges e, so e+1 must never land on bytes that the
+  // layout of e put into gather[parity of e] -- which a per-call offset would allow when the batch size changes
+  const size_t half = ((x->bytes_per_rank - MMF_XCHG_HEADER) / 2) & ~(size_t)1023;
+  if ((size_t)need > x->bytes_per_rank || (size_t)per_parity > half)
     return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_push: %lld bytes of peer buffer needed, %zu attached",
                          (long long)need, x->bytes_per_rank);
   const size_t local_bytes = (size_t)n_queries * k_local * 8;
@@ -223,13 +227,12 @@ extern "C" int mmf_vault_search_push(mmf_handle* h, const float* queries, int64_
     return mmf_set_error(h, MMF_ERR_NOMEM, "vault_search_push: local candidate buffer too small");
   const u32 epoch = x->epoch + 1;
   const int parity = (int)(epoch & 1u);
-  const size_t gather_off = MMF_XCHG_HEADER + (size_t)parity * (size_t)per_parity;
+  const size_t gather_off = MMF_XCHG_HEADER + (size_t)parity * half;
   const size_t slot_off = gather_off + (size_t)x->rank * local_bytes;
   // local search of this rank's shard -> packed candidates with GLOBAL row ids.
-  // MMF_EXCHANGE_FUSED=1 (experimental): the search writes them into this rank's own slot and, where its merge
+  // Option "fused_push" (default on): the search writes them into this rank's own slot and, where its merge
   // tail supports it (tcgen05 search, top_k > 16), pushes them to the peers and publishes the flags itself.
-  bool want_fused = false;
-  { const char* e = getenv("MMF_EXCHANGE_FUSED"); want_fused = e && atoi(e) != 0 && n_queries <= 65536; }
+  const bool want_fused = h->opt.fused_push != 0 && n_queries <= 65536;
   mmf_push_ctx ctx;
   memset(&ctx, 0, sizeof ctx);
   for (int r = 0; r < x->world; ++r) ctx.base[r] = x->peers.base[r];

@@ -20,12 +20,18 @@ struct FusionSmem {
   float b5[2];
 };
 
+// ASSEMBLE: the fusion inputs are built here as well (analyze()'s score assembly, misinfo_forensics.py:794-809):
+// x[s] = [ai, misinfo, deepfake, clip_sim, vault_disc] from head (n,3), sim (n), disc (n) with the scores of a skipped
+// modality zeroed (sim / disc masked in place, x written out) -- one launch instead of two for the batched path.
+template <bool ASSEMBLE>
 __global__ void __launch_bounds__(256) fusion_judge_kernel(const float* __restrict__ params,
                                                            const float* __restrict__ x,
                                                            const unsigned char* __restrict__ modality,
                                                            long long n, float* __restrict__ out_probs,
                                                            int* __restrict__ out_verdict,
-                                                           float* __restrict__ out_conf) {
+                                                           float* __restrict__ out_conf,
+                                                           const float* __restrict__ head, float* __restrict__ sim,
+                                                           float* __restrict__ disc, float* __restrict__ x_out) {
   __shared__ FusionSmem w;
   // params: [W0 (64,5) | b0 64 | W3 (32,64) | b3 32 | W5 (2,32) | b5 2]  (nn.Linear: weight (out,in))
   for (int i = threadIdx.x; i < 320; i += blockDim.x) w.w0t[i % 5][i / 5] = params[i];
@@ -39,11 +45,22 @@ __global__ void __launch_bounds__(256) fusion_judge_kernel(const float* __restri
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long s = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; s < n; s += warps) {
-    const float xl = (lane < 5) ? x[s * 5 + lane] : 0.f;
+    const int mod = modality ? modality[s] : 3;
+    float xl;
+    if (ASSEMBLE) {
+      const bool has_text = mod & 1, has_vis = mod & 2;
+      xl = 0.f;
+      if (lane < 2) xl = has_text ? head[s * 3 + lane] : 0.f;
+      else if (lane == 2) xl = has_vis ? head[s * 3 + 2] : 0.f;
+      else if (lane == 3) { xl = (has_text && has_vis) ? sim[s] : 0.f; sim[s] = xl; }   // analyze() skips the steps whose
+      else if (lane == 4) { xl = has_vis ? disc[s] : 0.f; disc[s] = xl; }               // modality is missing -> 0.0
+      if (lane < 5) x_out[s * 5 + lane] = xl;
+    } else {
+      xl = (lane < 5) ? x[s * 5 + lane] : 0.f;
+    }
     float xi[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) xi[i] = __shfl_sync(FULL, xl, i);
-    const int mod = modality ? modality[s] : 3;
     float real, fake;
     if (mod == 3) {                                   // warp-uniform: one sample per warp
       float h1a = w.b0[lane], h1b = w.b0[lane + 32];
@@ -93,7 +110,21 @@ static int fusion_launch(mmf_handle* h, const float* x, const uint8_t* modality,
   if (n == 0) return MMF_OK;
   const long long want = (n + 7) / 8;
   const int grid = (int)(want < (long long)h->sm_count * 4 ? want : (long long)h->sm_count * 4);
-  mmf::fusion_judge_kernel<<<grid, 256, 0, st>>>(h->fusion_params, x, modality, n, out_probs, out_verdict, out_conf);
+  mmf::fusion_judge_kernel<false><<<grid, 256, 0, st>>>(h->fusion_params, x, modality, n, out_probs, out_verdict, out_conf,
+                                                        nullptr, nullptr, nullptr, nullptr);
+  MMF_LAUNCH_OK(h);
+  return MMF_OK;
+}
+
+// score assembly + verdict in one launch (the batched host entry, api.cu); modality_in may be null (= both present)
+int mmf_assemble_verdict(mmf_handle* h, const float* head, const uint8_t* modality_in, int64_t n, float* sim, float* disc,
+                         float* x, float* out_probs, int32_t* out_verdict, float* out_conf, cudaStream_t st) {
+  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "assemble_verdict: fusion weights not loaded");
+  if (n <= 0) return MMF_OK;
+  const long long want = (n + 7) / 8;
+  const int grid = (int)(want < (long long)h->sm_count * 4 ? want : (long long)h->sm_count * 4);
+  mmf::fusion_judge_kernel<true><<<grid, 256, 0, st>>>(h->fusion_params, nullptr, modality_in, n, out_probs, out_verdict,
+                                                       out_conf, head, sim, disc, x);
   MMF_LAUNCH_OK(h);
   return MMF_OK;
 }

@@ -49,12 +49,13 @@
 // (mma_merge_kernel / mma_rerank_kernel: parallel slot gather, one staging sweep, rank-by-counting or radix
 // select) produces the final top-k per query from the strips' lists.
 //
-// Switches (environment, read per search; never needed in production -- INTEGRATION.md has the table):
-// MMF_MMA_SCREEN=0 (3-pass instead of screened), MMF_MMA_BOUND=pool (bucket maxima instead of the histogram),
-// MMF_MERGE_FAST=0 (first form of the tails); experiments not yet run on a GPU: MMF_MMA_STAGES=12, MMF_MMA_PREFETCH=1,
-// MMF_MMA_LEAN=1; triage: MMF_MMA_DEBUG (bit 0: skip the filter, 1: skip the vault TMA, 2: skip the MMA warp's
-// waits, 3: print in-kernel cycle counts), MMF_MMA_CG (force 1 or 2 CTAs per MMA), MMF_MMA_FLAT (plain
-// flattened schedule instead of the L2-aware one).
+// Switches: none are read from the environment on the search path.  mmf_set_option (include/mmf_b200.h) has "screen"
+// (0 = 3-pass kernel instead of the screened search, A/B + triage), "debug" (bit 0: skip the filter, 1: skip the vault
+// TMA, 2: skip the MMA warp's waits, 3: print in-kernel cycle counts), "force_cg" (1 or 2 CTAs per MMA) and
+// "flat_schedule" (plain flattened schedule instead of the L2-aware one).  Variants that lost their A/B on a B200 in
+// round 2 and were deleted: a 12-stage ring and an L2 prefetch for the screening pass (both slower: the loader is not
+// the limit, tools/tma_stream_micro.cu), the bucket-pool bound for top_k > 16 (histogram: 1.5x faster), the first
+// form of the merge / rerank tails.
 #include "common.cuh"
 #include "topk.cuh"
 
@@ -80,13 +81,9 @@ constexpr int Q_RESIDENT_BYTES = (MMF_DIM / KBLK) * TILE_BYTES;   // 128 KB
 // even when the data is there, against 256 clk of MMA work per k-block)
 __host__ __device__ constexpr int kblk_per_stage(bool split) { return split ? 1 : 2; }
 __host__ __device__ constexpr int stage_bytes(bool split, int cg) { return (split ? 2 : 1) * TILE_BYTES / cg * kblk_per_stage(split); }
-// deep (experimental, VAR_DEEP, pairs of the 1-plane pipeline only): 12 x 16 KB = 3 vault tiles in flight per CTA
-// instead of 2 -- the screening pass is HBM-latency-bound (ncu: DRAM 50 %, tensor pipe 58 %)
-__host__ __device__ constexpr int mma_stages(bool split, int cg, bool deep = false) {
-  return split ? 3 * cg : (cg == 1 ? 6 : (deep ? 12 : 8));
-}
-__host__ __device__ constexpr int mma_smem_bytes(bool split, int cg, bool deep = false) {
-  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg, deep) * stage_bytes(split, cg);
+__host__ __device__ constexpr int mma_stages(bool split, int cg) { return split ? 3 * cg : (cg == 1 ? 6 : 8); }
+__host__ __device__ constexpr int mma_smem_bytes(bool split, int cg) {
+  return (split ? Q_RESIDENT_BYTES : 0) + mma_stages(split, cg) * stage_bytes(split, cg);
 }
 constexpr int NUM_KBLK = MMF_DIM / KBLK;     // 8
 constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter: a lone warp per scheduler cannot hide its own latency
@@ -192,10 +189,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u64* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// L2 prefetch of one box of a 3-D tensor map: no shared memory, no barrier -- the data only moves DRAM -> L2
-__device__ __forceinline__ void tma_prefetch_l2_3d(const CUtensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -337,6 +330,17 @@ __host__ __device__ __forceinline__ float hist_edge(int bin) {   // lower edge o
 #endif
 }
 
+// ---- bucket pool (top_k <= 16) ---------------------------------------------------------------
+// bucket of a vault row: a hash of the row id onto [0, top_k).  Every bucket keeps the best score key seen among
+// ITS rows (atomicMax), the buckets partition the rows, so the minimum over the top_k bucket maxima is attained
+// by top_k distinct rows: a lower bound of the top_k-th best.  With exactly top_k buckets it sits near rank
+// top_k * H(top_k) of the rows seen grid-wide (29 for top_k = 10, 11 for top_k = 5; the 16 buckets of round 1: 54).
+// Hashed, not row % top_k: the rows of a tile are consecutive, and the order statistics argument wants the
+// buckets of a tile's rows to be independent of the tile.
+__host__ __device__ __forceinline__ u32 pool_bucket(u32 row, u32 top_k) {
+  return (((row * 0x9E3779B1u) >> 16) * top_k) >> 16;
+}
+
 // ---- query operand prep --------------------------------------------------------------------
 // One warp per padded query row: q / ||q|| (misinfo_forensics.py:439), then the MMA operand
 // planes: bf16 (1 plane) or fp16 hi/lo of q*2^8 (2 planes, plane p at row p*q_pad + i).
@@ -347,8 +351,7 @@ __device__ __forceinline__ void prep_query_row(const float* __restrict__ q, int 
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q_pad) return;
   if (lane == 0) g_tau[w] = 0;
-  int pool_n = 16;                                // buckets: power of two >= top_k (>= 16)
-  while (pool_n < top_k) pool_n <<= 1;
+  const int pool_n = top_k;                       // bucket pool (top_k <= 16): exactly top_k buckets, the rest never win the min
 #pragma unroll
   for (int j = 0; j < MMF_MAX_TOP_K / 32; ++j)   // unused buckets never win the min
     pool[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (hist || j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
@@ -376,36 +379,28 @@ __device__ __forceinline__ void prep_query_row(const float* __restrict__ q, int 
     }
   }
 }
+// The ONE preparation launch of a search: normalised query planes, cleared bounds, cleared candidate counters
+// (zero[0..zero_n): the counters of this search and, for the screened search, the overflow flag and the counters
+// of the guarded pass) and -- screened search only -- a second set of bounds for the guarded exact pass (bucket
+// pool, top_k <= 16), so that a screened search is 5 launches and no memset.
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
                                                              int split, void* __restrict__ planes,
                                                              u32* __restrict__ g_tau, u32* __restrict__ pool,
-                                                             int top_k, int hist, float* __restrict__ qn) {
-  prep_query_row(q, n_queries, q_pad, split, planes, g_tau, pool, top_k, hist, qn);
-}
-// LEAN launch sequence of the screened search (experimental, env MMF_MMA_LEAN=1): the prep kernel also clears the
-// candidate counters of both passes and the overflow flag (instead of three memsets) and initialises a SECOND set
-// of bounds for the guarded exact pass (instead of a second prep launch), so a search is 5 launches, not 9 stream
-// operations.
-__global__ void __launch_bounds__(256) mma_query_prep_lean_kernel(const float* __restrict__ q, int n_queries, int q_pad,
-                                                                  void* __restrict__ planes, u32* __restrict__ g_tau,
-                                                                  u32* __restrict__ pool, int top_k, float* __restrict__ qn,
-                                                                  int* __restrict__ zero_a, long long zero_a_n,
-                                                                  int* __restrict__ zero_b, long long zero_b_n,
-                                                                  u32* __restrict__ g_tau2, u32* __restrict__ pool2) {
+                                                             int top_k, int hist, float* __restrict__ qn,
+                                                             int* __restrict__ zero, long long zero_n,
+                                                             u32* __restrict__ g_tau2, u32* __restrict__ pool2) {
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
-  for (long long i = gtid; i < zero_a_n; i += nthr) zero_a[i] = 0;
-  for (long long i = gtid; i < zero_b_n; i += nthr) zero_b[i] = 0;
+  for (long long i = gtid; i < zero_n; i += nthr) zero[i] = 0;
   const int lane = threadIdx.x & 31;
   const int w = (int)(gtid >> 5);
-  if (w < q_pad) {                                  // bounds of the guarded pass: bucket pool (top_k <= 16)
+  if (g_tau2 && w < q_pad) {
     if (lane == 0) g_tau2[w] = 0;
-    int pool_n = 16;
-    while (pool_n < top_k) pool_n <<= 1;
+    const int pool_n = top_k;
 #pragma unroll
     for (int j = 0; j < MMF_MAX_TOP_K / 32; ++j)
       pool2[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
   }
-  prep_query_row(q, n_queries, q_pad, 1, planes, g_tau, pool, top_k, 0, qn);
+  prep_query_row(q, n_queries, q_pad, split, planes, g_tau, pool, top_k, hist, qn);
 }
 
 // ---- the search kernel ---------------------------------------------------------------------
@@ -413,50 +408,46 @@ __global__ void __launch_bounds__(256) mma_query_prep_lean_kernel(const float* _
 // M = 256 = two query tiles, one per CTA); each CTA streams and stores only half of every vault
 // tile, which halves the shared-memory traffic per flop -- measured, shared-memory bandwidth (TMA
 // fill + tensor-core operand fetch = 128 B/clk) is what bounds the CG = 1 kernel.
-// KR > 0 (top_k <= KR): every epilogue thread also keeps the KR best accumulator values of its list
-// sorted in registers, so its threshold is EXACT at all times (the k-th best of everything it has
-// seen) instead of being refreshed only when the list is compacted; far fewer candidates pass and
-// short lists never need a compaction.  KR = 0: lazy thresholds (large top_k).
-// HIST (KR == 0 only, experimental, env MMF_MMA_BOUND=hist): the grid-wide bound comes from a per-query
-// HISTOGRAM of candidate scores instead of the bucket maxima.  The minimum over top_k bucket maxima sits
-// near rank top_k * H(top_k) (~700 for top_k = 100), so ~7x more elements pass the filter than a tight
-// bound would let through; the histogram bound sits at the lower edge of the bin holding the k-th best
-// counted candidate (bins = 1/32 of an octave: rank <~ 1.4 * top_k).
+// KR > 0 (top_k <= KR = 16): grid-wide bound from the BUCKET POOL (pool_bucket above): a thread appends an element
+// when it is not below the minimum over its query's top_k bucket maxima.  (Round 1 also kept the KR best values
+// of every list sorted in registers; measured in round 2, a list's own k-th best -- of 1/148 of the rows -- never
+// beats the pool after the first chunk of a strip, while the sorted insert was half of a candidate event's ~70
+// instructions and the events were 70 % of all epilogue instructions.  Removed: 0.308 -> 0.293 ms on C2.)
+// KR == 0 bounds the k-th best grid-wide with a per-query HISTOGRAM of candidate scores: the lower edge of the bin
+// holding the k-th best counted candidate (bins = 1/32 of an octave: rank <~ 1.4 * top_k; the minimum over top_k
+// bucket maxima sits near rank top_k * H(top_k), ~700 for top_k = 100, and let ~7x more elements through).
 //
-// VAR_SCREEN (fp32-exact vaults, top_k <= 16, experimental, env MMF_MMA_SCREEN=1): ONE f16 pass over the hi
-// planes only (qh.vh: a third of the tensor work and half of the HBM bytes of the 3-pass kernel) gives
-// scores within a PROVEN error bound eps of the exact ones; every element within 2*eps of the running
-// k-th best is kept, and mma_rerank_kernel re-scores the survivors exactly in fp32 from the hi+lo planes
-// and selects the top-k among them -- the result is the exact top-k, not an approximation.
-// If a band does not fit a candidate list, *p.ovf is set and the guarded (VAR_GUARD) 3-pass kernel redoes
-// the batch.
-// VAR_PREFETCH (experimental, screening pass, env MMF_MMA_PREFETCH=1): the producer asks for the vault tile it will
-// need PREFETCH_TILES tiles from now to be pulled into L2 (cp.async.bulk.prefetch.tensor), so that the DRAM latency
-// is hidden by L2 capacity (a few MB per SM-pair in flight) instead of by the 2-tile shared-memory ring.
-constexpr int VAR_HIST = 1, VAR_SCREEN = 2, VAR_GUARD = 4, VAR_DEEP = 8, VAR_PREFETCH = 16;
-constexpr int PREFETCH_TILES = 4;
+// VAR_SCREEN (fp32-exact vaults, top_k <= 16): ONE f16 pass over the hi planes only (qh.vh: a third of the tensor
+// work and half of the HBM bytes of the 3-pass kernel) gives scores within a PROVEN error bound eps of the exact
+// ones; every element within 2*eps of the running k-th best is kept, and mma_rerank_kernel re-scores the survivors
+// exactly in fp32 from the hi+lo planes and selects the top-k among them -- the result is the exact top-k, not an
+// approximation.  If a band does not fit a candidate list, *p.ovf is set and the guarded (VAR_GUARD)
+// 3-pass kernel redoes the batch.
+// VAR_PARITY (KR > 0 only): how the 8 epilogue warps share the accumulators, see PARITY below.
+constexpr int VAR_SCREEN = 2, VAR_GUARD = 4, VAR_PARITY = 8;
 template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                       const MmaParams p) {
-  constexpr int STAGES = mma_stages(SPLIT, CG, (VAR & VAR_DEEP) != 0);
+  constexpr int STAGES = mma_stages(SPLIT, CG);
   constexpr int STAGE_BYTES = stage_bytes(SPLIT, CG);
   constexpr int KBS = kblk_per_stage(SPLIT);         // k-blocks per stage
   constexpr int PLANE_BYTES = TILE_BYTES / CG;       // one plane of this CTA's share of a B k-block
   constexpr int KB_BYTES = STAGE_BYTES / KBS;        // one k-block (all planes) inside a stage
   constexpr int B_ROWS = TILE_N / CG;
   constexpr int C = 32 * KPL;
-  constexpr bool HIST = (VAR & VAR_HIST) != 0, SCREEN = (VAR & VAR_SCREEN) != 0, GUARD = (VAR & VAR_GUARD) != 0;
-  static_assert(!(SCREEN && (SPLIT || KR == 0)), "the screening pass is the 1-plane pipeline with exact register thresholds");
+  constexpr bool HIST = KR == 0, SCREEN = (VAR & VAR_SCREEN) != 0, GUARD = (VAR & VAR_GUARD) != 0;
+  static_assert(!(SCREEN && (SPLIT || KR == 0)), "the screening pass is the 1-plane pipeline with the bucket-pool bound");
   constexpr u32 IDESC = umma_idesc((SPLIT || SCREEN) ? 0u : 1u, TILE_M * CG, TILE_N);   // operands: fp16 planes / bf16
   constexpr u32 QA_COL = 2 * TILE_N;                 // TMEM columns [256,512): plane 0 of the query tile
-  // How the 8 epilogue warps share the accumulators.  PARITY (small top_k, short per-tile work): warps
-  // 0-3 own buffer 0 (even tiles), warps 4-7 buffer 1 -- two tile periods per tile hide the hand-off
-  // latencies.  Otherwise (large top_k: many candidate events per tile) both warps of a lane quarter
-  // work on EVERY tile, alternate 32-column chunks each, so an accumulator is released after half the
-  // filtering time -- the MMAs of tile i+2 wait for exactly that.
-  constexpr bool PARITY = KR > 0;
-  static_assert(!(HIST && KR > 0), "the histogram bound replaces the bucket pool of the lazy-threshold (KR == 0) variants only");
+  // How the 8 epilogue warps share the accumulators.  PARITY: warps 0-3 own buffer 0 (even tiles), warps 4-7
+  // buffer 1 -- two tile periods per tile hide the hand-off latencies; right when a tile's MMAs take much longer
+  // than its filtering (the 3-pass fp32-exact kernel: 6144 clk of MMA per tile).  Otherwise both warps of a lane
+  // quarter work on EVERY tile, alternate 32-column chunks each, so an accumulator is released after half the
+  // filtering time -- the MMAs of tile i+2 wait for exactly that.  Measured on the screening pass (2048 clk of MMA
+  // per tile): one warp set needs ~2900 clk per tile (a lone warp per scheduler retires an instruction every
+  // 4-5 clk), so with PARITY the tensor pipe waited 1400 clk per tile for its accumulator.
+  constexpr bool PARITY = KR > 0 && (VAR & VAR_PARITY) != 0;
   constexpr int EMPTY_ARRIVALS = (PARITY ? EPI_WARPS / 2 : EPI_WARPS) * CG;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -528,14 +519,6 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           ++strip;
         }
         const int brow = vt * TILE_N + (int)rank * B_ROWS;
-        if constexpr ((VAR & VAR_PREFETCH) != 0 && (VAR & VAR_SCREEN) != 0) {
-          // same strip, PREFETCH_TILES ahead (the few tiles around a strip change simply go unprefetched)
-          if (u + PREFETCH_TILES < sch.n_tiles && vt + PREFETCH_TILES < sch.v_hi) {
-            const int prow = (vt + PREFETCH_TILES) * TILE_N + (int)rank * B_ROWS;
-#pragma unroll
-            for (int kb = 0; kb < NUM_KBLK; ++kb) tma_prefetch_l2_3d(&tm_b, kb * KBLK, 0, prow);
-          }
-        }
         for (int kb = 0; kb < NUM_KBLK; kb += KBS, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
@@ -659,13 +642,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     const u32 tmem_empty_l = (CG == 2) ? mapa(smem_u32(tmem_empty), 0) : smem_u32(tmem_empty);
     const u32 qa_full_l = (CG == 2) ? mapa(smem_u32(qa_full), 0) : smem_u32(qa_full);
     const int k = p.top_k;
-    u32 pool_mask = 15;                               // buckets - 1: power of two >= top_k, so that the
-    while ((int)pool_mask + 1 < k) pool_mask = 2 * pool_mask + 1;   // min over buckets bounds the k-th best
     const float acc_scale = 1.0f / p.inv_scale;
     const float margin_acc = SCREEN ? p.margin * acc_scale : 0.f;   // candidate band in accumulator units
 #define MMF_TAU_F (SCREEN ? tau_acc - margin_acc : tau_acc)       /* what the filter compares against */
     float tau_acc = -INFINITY;                        // threshold in accumulator units
-    float best[KR > 0 ? KR : 1];                      // KR > 0: the KR best accumulators, descending
     int cnt = 0;
     int cur_tp = -1;
     u64* buf = nullptr;
@@ -675,6 +655,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     uint4 pool_prev[4];
     bool valid_q = false;
     u32 tile = 0, g_prev = 0;
+    int strip_u0 = 0;                                 // first tile of the current strip (warm-up: see the chunk loop)
     const bool dbg = (p.debug & 8) != 0;
     long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
     int dbg_ncompact = 0;
@@ -689,6 +670,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
         }
         cur_tp = tp;
+        strip_u0 = u;
         cnt = 0;
         g_prev = 0;
         tau_acc = -INFINITY;
@@ -702,9 +684,6 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         if (KR > 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) pool_prev[i] = make_uint4(0, 0, 0, 0);
-          // slots beyond top_k hold +inf "phantoms", so best[KR-1] is always the top_k-th best
-#pragma unroll
-          for (int i = 0; i < KR; ++i) best[i] = (i < KR - k) ? INFINITY : -INFINITY;
         }
         {
           // this thread's query row of plane 0 -> its TMEM lane, 2 elements per column (each warp of
@@ -748,15 +727,49 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       tcgen05_fence_after();
       const long long t_w1 = dbg ? clock64() : 0;
       dbg_wait += t_w1 - t_w0;
+      // (segment g of the L2-aware schedule holds one pair per query-tile group: every 8th segment is designated)
+      const bool storm_pair = pair < p.n_aligned ? (((pair / p.qtp) & 7) == 0) : (p.n_aligned == 0);
+      if (KR > 0 && u == strip_u0 && !storm_pair && !(p.debug & 64)) {
+        // Warm-up of a strip.  With no bound yet, every element of the first chunk is a candidate event (a store
+        // and an atomic, 32 distinct lines each per warp instruction), in every block at once: measured on the
+        // screening pass, the first two tiles cost 55k of 347k clk, most of it contention on the 10 pool words per
+        // query.  One storm per QUERY is enough to seed the pool, so only every 8th pair takes it; the others wait
+        // here (bounded) until all of their query's buckets are filled, and start with the grid-wide bound.
+        const long long t_end = clock64() + 30000;
+        for (;;) {
+          u32 mn = 0xFFFFFFFFu;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool) + i);
+            mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
+          }
+          if (mn != 0u) { tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale); break; }
+          if (!valid_q || clock64() > t_end) break;
+          __nanosleep(400);
+        }
+        __syncwarp();
+      }
       const long long row0 = (long long)vt * TILE_N;
       const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
       const bool partial = n_cols < TILE_N;           // beyond n_cols the tile is TMA zero fill
       const u32 row_id0 = p.row_base + (u32)row0;
-      bool improved = false;
 #pragma unroll 1
       for (int c = PARITY ? 0 : half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += PARITY ? 1 : 2) {
         u32 v[32];
         tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
+        if (KR > 0 && u - strip_u0 < (PARITY ? 4 : 2) && (u != strip_u0 || c >= 2)) {
+          // warm-up of a strip: a list's own threshold is still loose (the 10th best of a few dozen rows) while the
+          // whole grid has already seen thousands, so re-read the bucket pool before EVERY chunk of the first two
+          // tiles instead of once per tile -- 22 + 0.2 candidate events per thread in tile 0 instead of 22 + 7, and
+          // a candidate event costs ~70 instructions for the whole warp.  (The loads overlap the tcgen05.ld.)
+          u32 mn = 0xFFFFFFFFu;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool) + i);
+            mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
+          }
+          if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
+        }
         tmem_wait_ld();
         // fast path (almost always): chunk maximum below the threshold.  A max tree keeps the
         // dependent chain short.  (fmaxf drops a NaN next to a number; vaults with NaN rows never
@@ -767,7 +780,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        if (!(m8 < MMF_TAU_F) && valid_q) {
+        if (p.debug & 16) { if (m8 == 12345.678f) cnt = 1; continue; }      // triage: tcgen05.ld + max tree only
+        if (!(m8 < MMF_TAU_F) && valid_q && !((p.debug & 32) && u - strip_u0 >= 2)) {   // triage bit 5: no events after the warm-up tiles
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (!(mx[i] < MMF_TAU_F)) {
@@ -787,14 +801,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
                     const int bin = hist_bin(ub);
                     if (bin > 0) atomicAdd(pool + bin, 1u);     // bin 0 (score < 2^-7) carries no bound
                   } else {
-                    atomicMax(pool + (row & pool_mask), key);
-                  }
-                  if (KR > 0) {
-                    // sorted insert, branch free: new[i] = max(old[i], min(old[i-1], a))
-#pragma unroll
-                    for (int j = KR - 1; j > 0; --j) best[j] = fmaxf(best[j], fminf(best[j - 1], a));
-                    best[0] = fmaxf(best[0], a);
-                    if (best[KR - 1] > tau_acc) { tau_acc = best[KR - 1]; improved = true; }
+                    atomicMax(pool + pool_bucket(row, (u32)k), key);
                   }
                 }
               }
@@ -808,7 +815,6 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
-      if (KR > 0 && improved) atomicMax(g_tau, okey(tau_acc * p.inv_scale));
       if (KR == 0 && valid_q && (tile < 96 ? (tile & 3) == 3 : (tile & 31) == 31)) {
         // large top_k: refresh the grid-wide bound from the bucket pool -- every 4th tile while the
         // thresholds still move fast (half of all candidate events happen in the first few thousand rows),
@@ -842,13 +848,6 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
               atomicMax(g_tau, okey(edge));
             }
           }
-        } else {
-          u32 mn = 0xFFFFFFFFu;
-          for (int j = 0; j <= (int)pool_mask; j += 4) {
-            const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool + j));
-            mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
-          }
-          if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
         }
       }
       // keep room for one more tile (ROOM appends per thread); warp-cooperative, one list at a time
@@ -893,33 +892,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 }
 
 // Slots (strip * 2 + column half) of the candidate lists that cover query-tile group `tp`: every pair whose
-// schedule touches the group contributes its strip.  Thread 0 only; `slots` / `n_slots` in shared memory.
+// schedule touches the group contributes its strip.  One pair per thread; *n_slots must be 0 (and a barrier
+// passed) on entry; may end up > MERGE_MAX_SLOTS, only the first MERGE_MAX_SLOTS entries are written.  The order of
+// the slots depends on the schedule of the atomics; the selection that follows does not.
 constexpr int MERGE_MAX_SLOTS = 4 * 160;
-__device__ __forceinline__ void gather_slots(const MmaParams& p, int n_pairs, int tp, int* slots, int* n_slots) {
-  int n = 0;
-  for (int c = 0; c < n_pairs; ++c) {
-    const PairSchedule sc = pair_schedule(p, c, n_pairs);
-    if (sc.n_tiles <= 0) continue;
-    bool touches;
-    if (c < p.n_aligned) {
-      touches = sc.tp0 == tp;
-    } else {
-      const int vl = sc.v_hi - sc.v_lo;
-      const long long first = (long long)sc.tp0 * vl + (sc.vt0 - sc.v_lo), last = first + sc.n_tiles - 1;
-      touches = vl > 0 && first / vl <= tp && tp <= last / vl;
-    }
-    if (touches && n + 2 <= MERGE_MAX_SLOTS) {
-      slots[n++] = (sc.sid_base + tp) * 2;
-      slots[n++] = (sc.sid_base + tp) * 2 + 1;
-    }
-  }
-  *n_slots = n;
-}
-
-// The same, one pair per thread (FAST tails): thread 0's serial loop over the pairs -- two 64-bit divisions
-// per pair -- was the longest single piece of the merge / rerank kernels.  *n_slots must be 0 (and a barrier
-// passed) on entry; may end up > MERGE_MAX_SLOTS, only the first MERGE_MAX_SLOTS entries are written.  The
-// order of the slots depends on the schedule of the atomics; the selection that follows does not.
 __device__ __forceinline__ void gather_slots_par(const MmaParams& p, int n_pairs, int tp, int* slots, int* n_slots) {
   for (int c = threadIdx.x; c < n_pairs; c += blockDim.x) {
     const PairSchedule sc = pair_schedule(p, c, n_pairs);
@@ -942,103 +918,83 @@ __device__ __forceinline__ void gather_slots_par(const MmaParams& p, int n_pairs
   }
 }
 
-// One block per query: gather the strips that cover its query tile, select + sort the top-k.
-// GUARD: runs only when the screened search flagged an overflow (*p.ovf != 0).
-// FAST (default; MMF_MERGE_FAST=0 = the first form): parallel slot gather; stage once, then rank-by-counting when few
-// candidates were staged (the usual case for small top_k) instead of 8 radix passes + a bitonic sort.
-template <int KPL, int CG, bool GUARD = false, bool FAST = false>
-__global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
-                                                        float* out_scores, long long* out_rows, u64* out_packed,
-                                                        float* out_disc) {
+// Shared front half of the tail kernels: the candidate lists of query `qg` as a CandidateLists view.
+// slots / n_slots: shared memory of the calling block.  All threads must call it.
+template <int KPL, int CG>
+__device__ __forceinline__ CandidateLists lists_of_query(const MmaParams& p, int n_pairs, int qg, int* slots, int* n_slots) {
   constexpr int C = 32 * KPL;
-  __shared__ SelectSmem sel;
-  __shared__ u64 staging[4096];
-  __shared__ int slots[MERGE_MAX_SLOTS];  // (strip, half) slots holding lists of this query's tile group
-  __shared__ int n_slots;
-  if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
-  const int qg = blockIdx.x;
   const int qt = qg / TILE_M, m = qg % TILE_M;
   const int tp = qt / CG, r = qt % CG;
-  if (FAST) {
-    if (threadIdx.x == 0) n_slots = 0;
-    __syncthreads();
-    gather_slots_par(p, n_pairs, tp, slots, &n_slots);
-  } else {
-    if (threadIdx.x == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
-  }
+  if (threadIdx.x == 0) *n_slots = 0;
+  __syncthreads();
+  gather_slots_par(p, n_pairs, tp, slots, n_slots);
   __syncthreads();
   // lists of this query: [strip][half][r][m][C]; slot = strip*2 + half selects a block of CG*TILE_M lists
   CandidateLists src;
   const long long base = (long long)r * TILE_M + m;
   src.lists = p.cand + base * C;
   src.counts = p.cand_cnt + base;
-  src.n_lists = FAST ? min(n_slots, MERGE_MAX_SLOTS) : n_slots;
+  src.n_lists = min(*n_slots, MERGE_MAX_SLOTS);
   src.k_in = C;
   src.list_stride = (long long)CG * TILE_M * C;
   src.count_stride = CG * TILE_M;
   src.slots = slots;
-  if (FAST) {
-    float* os = out_scores ? out_scores + (long long)qg * p.top_k : nullptr;
-    long long* orow = out_rows ? out_rows + (long long)qg * p.top_k : nullptr;
-    u64* op = out_packed ? out_packed + (long long)qg * p.top_k : nullptr;
-    float* od = out_disc ? out_disc + qg : nullptr;
-    const u32 n = stage_candidates(src, sel, staging, 4096, (u64)p.g_tau[qg] << 32);
-    if (n <= (u32)RANK_SELECT_MAX) {
-      block_rank_select(staging, (int)n, p.top_k, sel);
-      write_topk_outputs(sel, p.top_k, os, orow, op, od, threshold);
-    } else if (n <= 4096u) {          // staged: radix select over the staged keys, read in place
-      CandidateLists ex;
-      ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n; ex.list_stride = 0; ex.count_stride = 0;
-      block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, os, orow, op, od, threshold);
-    } else {                          // does not fit: the general path re-reads global memory
-      block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, os, orow, op, od, threshold);
-    }
-    return;
-  }
-  block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32,
-                    out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
-                    out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
-                    out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
-                    threshold);
+  return src;
 }
 
-// Merge tail fused with the candidate push of the row-sharded search (experimental, MMF_EXCHANGE_FUSED=1; see
-// exchange.cu for the protocol): the FAST merge of one query, then its top_k winners go straight from shared
-// memory into slot [rank] of EVERY rank's gather buffer (the own one included) -- the transfer of query i overlaps
-// the selection of the other queries -- and the last block publishes this rank's epoch flag on every rank.
-template <int KPL, int CG>
-__global__ void __launch_bounds__(256) mma_merge_push_kernel(const MmaParams p, int n_pairs, const mmf_push_ctx px) {
-  constexpr int C = 32 * KPL;
-  __shared__ SelectSmem sel;
-  __shared__ u64 staging[4096];
-  __shared__ int slots[MERGE_MAX_SLOTS];
-  __shared__ int n_slots;
-  __shared__ bool last;
-  const int qg = blockIdx.x;
-  const int qt = qg / TILE_M, m = qg % TILE_M;
-  const int tp = qt / CG, r = qt % CG;
-  if (threadIdx.x == 0) n_slots = 0;
-  __syncthreads();
-  gather_slots_par(p, n_pairs, tp, slots, &n_slots);
-  __syncthreads();
-  CandidateLists src;
-  const long long base = (long long)r * TILE_M + m;
-  src.lists = p.cand + base * C;
-  src.counts = p.cand_cnt + base;
-  src.n_lists = min(n_slots, MERGE_MAX_SLOTS);
-  src.k_in = C;
-  src.list_stride = (long long)CG * TILE_M * C;
-  src.count_stride = CG * TILE_M;
-  src.slots = slots;
-  const u32 n = stage_candidates(src, sel, staging, 4096, (u64)p.g_tau[qg] << 32);
+// Best published lower bound (score key) of query qg's top_k-th best: g_tau, and for top_k <= 16 (bucket-pool kernels)
+// the minimum over the 16 bucket maxima -- 16 distinct rows score at least that.  0 = no bound.
+__device__ __forceinline__ u32 published_bound(const MmaParams& p, int qg) {
+  u32 g = p.g_tau[qg];
+  if (p.top_k <= 16) {
+    u32 mn = 0xFFFFFFFFu;
+    for (int j = 0; j < 16; ++j) mn = min(mn, p.pool[(long long)qg * MMF_MAX_TOP_K + j]);   // broadcast loads
+    g = max(g, mn);                                                                          // (an empty bucket is 0)
+  }
+  return g;
+}
+
+// sm.win[0..top_k) := the top_k best of the staged keys (n of them; in staging[] if n <= cap, else the general path
+// re-reads the lists).  Rank-by-counting when few were staged (the usual case), radix select otherwise.
+__device__ __forceinline__ void select_staged(const CandidateLists& src, u32 n, u64* staging, int cap, u64 min_key, int top_k,
+                                              SelectSmem& sel) {
   if (n <= (u32)RANK_SELECT_MAX) {
-    block_rank_select(staging, (int)n, p.top_k, sel);
-  } else if (n <= 4096u) {
+    block_rank_select(staging, (int)n, top_k, sel);
+  } else if (n <= (u32)cap) {         // staged: radix select over the staged keys, read in place
     CandidateLists ex;
     ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n; ex.list_stride = 0; ex.count_stride = 0;
-    block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, 0.0);
-  } else {
-    block_select_topk(src, p.top_k, sel, staging, 4096, (u64)p.g_tau[qg] << 32, nullptr, nullptr, nullptr, nullptr, 0.0);
+    block_select_topk(ex, top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, 0.0);
+  } else {                            // does not fit: the general path re-reads global memory
+    block_select_topk(src, top_k, sel, staging, cap, min_key, nullptr, nullptr, nullptr, nullptr, 0.0);
+  }
+}
+
+// One block per query: gather the strips that cover its query tile, select + sort the top-k.
+// GUARD: runs only when the screened search flagged an overflow (*p.ovf != 0).
+// PUSH: row-sharded search over peer memory (exchange.cu): instead of writing outputs, the top_k winners go straight
+// from shared memory into slot [rank] of EVERY rank's gather buffer (the own one included) -- the NVLink transfer of
+// query i overlaps the selection of the other queries -- and the last block publishes this rank's epoch flag.
+template <int KPL, int CG, bool GUARD, bool PUSH>
+__global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
+                                                        float* out_scores, long long* out_rows, u64* out_packed,
+                                                        float* out_disc, const mmf_push_ctx px) {
+  __shared__ SelectSmem sel;
+  __shared__ u64 staging[4096];
+  __shared__ int slots[MERGE_MAX_SLOTS];  // (strip, half) slots holding lists of this query's tile group
+  __shared__ int n_slots;
+  __shared__ bool last;
+  if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
+  const int qg = blockIdx.x;
+  const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
+  const u64 min_key = (u64)published_bound(p, qg) << 32;
+  const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
+  select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
+  if (!PUSH) {
+    write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+                       out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
+                       out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
+                       threshold);
+    return;
   }
   // sel.win[0..top_k): this query's winners, sorted (0 = empty).  Push them to every rank.
   for (int i = threadIdx.x; i < p.top_k * px.world; i += blockDim.x) {
@@ -1063,8 +1019,8 @@ __global__ void __launch_bounds__(256) mma_merge_push_kernel(const MmaParams p, 
 
 // Screened search, second half (VAR_SCREEN): one block per query.
 //   1. stage every candidate of the query whose APPROXIMATE score lies within the band below the grid-wide
-//      bound, and select the approximate top-k among them (block_select_topk, no outputs): its k-th entry T
-//      is the exact k-th best approximate score of the whole shard;
+//      bound, and select the approximate top-k among them: its k-th entry T is the exact k-th best approximate
+//      score of the whole shard;
 //   2. every staged candidate with score >= T - margin is re-scored EXACTLY: fp32 dot of the fp32-normalised
 //      query with hi + lo of the vault row -- the arithmetic of the streaming kernel (vault_stream.cu), so the
 //      reported scores are bit-identical to a batch-1 search; the others are dropped;
@@ -1072,63 +1028,31 @@ __global__ void __launch_bounds__(256) mma_merge_push_kernel(const MmaParams p, 
 // Why this is the exact top-k: |approx - exact| <= eps = margin / 2 for every row.  k rows have approx >= T,
 // hence exact >= T - eps, so the exact k-th best is >= T - eps, and a row of the exact top-k has
 // approx >= T - 2 eps -- it is among the re-scored ones.
-template <int KPL, int CG, bool FAST = false>
+// The staging bound is the better of g_tau (the best per-list k-th best) and the minimum over the bucket pool (a
+// grid-wide bound near rank 54 for top_k = 10): with g_tau alone ~700 candidates per query were staged and the
+// selection ran 8 radix passes; with the pool a few dozen are, and rank-by-counting does it in two barriers.
+template <int KPL, int CG>
 __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int n_pairs, double threshold,
                                                          const uint4* __restrict__ vault, float* out_scores,
                                                          long long* out_rows, u64* out_packed, float* out_disc) {
-  constexpr int C = 32 * KPL;
   constexpr int STAGING = 4096;
   __shared__ SelectSmem sel;
   __shared__ u64 staging[STAGING];
   __shared__ int slots[MERGE_MAX_SLOTS];
   __shared__ int n_slots;
   const int qg = blockIdx.x;
-  const int qt = qg / TILE_M, m = qg % TILE_M;
-  const int tp = qt / CG, r = qt % CG;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (FAST) {
-    if (tid == 0) n_slots = 0;
-    __syncthreads();
-    gather_slots_par(p, n_pairs, tp, slots, &n_slots);
-  } else {
-    if (tid == 0) gather_slots(p, n_pairs, tp, slots, &n_slots);
-  }
-  __syncthreads();
-  CandidateLists src;
-  const long long base = (long long)r * TILE_M + m;
-  src.lists = p.cand + base * C;
-  src.counts = p.cand_cnt + base;
-  src.n_lists = FAST ? min(n_slots, MERGE_MAX_SLOTS) : n_slots;
-  src.k_in = C;
-  src.list_stride = (long long)CG * TILE_M * C;
-  src.count_stride = CG * TILE_M;
-  src.slots = slots;
-  // g_tau bounds the k-th best APPROXIMATE score from below; candidates down to margin below it may matter
-  const u32 g = p.g_tau[qg];
+  // bounds on the k-th best APPROXIMATE score; candidates down to margin below it may matter
+  const u32 g = published_bound(p, qg);
   const u64 min_key = g ? (u64)okey(okey_inv(g) - p.margin) << 32 : 0ull;
-  u32 n_staged;
-  if (FAST) {
-    n_staged = stage_candidates(src, sel, staging, STAGING, min_key);
-  } else {
-    block_select_topk(src, p.top_k, sel, staging, STAGING, min_key, nullptr, nullptr, nullptr, nullptr, threshold);
-    n_staged = sel.n_staged;
-  }
+  const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
+  const u32 n_staged = stage_candidates(src, sel, staging, STAGING, min_key);
   if (n_staged > (u32)STAGING || n_slots >= MERGE_MAX_SLOTS) {   // band too wide to stage: exact redo of the batch
     if (tid == 0) *p.ovf = 1;
     return;
   }
-  CandidateLists ex;                                             // the staged keys as one list, read in place
-  ex.lists = staging;
-  ex.counts = nullptr;
-  ex.n_lists = 1;
-  ex.k_in = (int)n_staged;
-  ex.list_stride = 0;
-  ex.count_stride = 0;
-  const bool by_rank = FAST && n_staged <= (u32)RANK_SELECT_MAX;
-  if (FAST) {                                                    // approximate top-k of the staged candidates
-    if (by_rank) block_rank_select(staging, (int)n_staged, p.top_k, sel);
-    else block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, threshold);
-  }
+  const bool by_rank = n_staged <= (u32)RANK_SELECT_MAX;
+  select_staged(src, n_staged, staging, STAGING, min_key, p.top_k, sel);      // approximate top-k of the staged candidates
   const u64 kth = sel.win[p.top_k - 1];                          // 0: fewer than top_k candidates -> keep all
   const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - p.margin) << 32 : 0ull;
   __syncthreads();
@@ -1169,19 +1093,18 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
     if (lane == 0) staging[i] = exact;
   }
   __syncthreads();
-  // select + sort the exact keys: one list in shared memory (staging_cap 0: the passes read it in place)
+  // select + sort the exact keys: one list in shared memory, read in place
   if (by_rank) {
     block_rank_select(staging, (int)n_staged, p.top_k, sel);
-    write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
-                       out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
-                       out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
-                       threshold);
-    return;
+  } else {
+    CandidateLists ex;
+    ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n_staged; ex.list_stride = 0; ex.count_stride = 0;
+    block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, 0.0);
   }
-  block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
-                    out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
-                    out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
-                    threshold);
+  write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
+                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
+                     threshold);
 }
 
 }  // namespace mmf
@@ -1260,10 +1183,11 @@ void mmf_mma_destroy(mmf_handle* h) {
 }
 
 // Work decomposition of one search: CTAs per MMA, padded query tiles, vault tiles, schedule.
-static void mma_plan(int64_t n_queries, int64_t n_rows, int sm_count, MmaParams& p, int& cg, int& n_pairs) {
+static void mma_plan(int64_t n_queries, int64_t n_rows, int sm_count, MmaParams& p, int& cg, int& n_pairs,
+                     int force_cg = 0, bool flat = false) {
   // a thread-block pair per MMA as soon as there are two query tiles to pair up
   cg = n_queries > TILE_M ? 2 : 1;
-  { const char* e = getenv("MMF_MMA_CG"); if (e && (atoi(e) == 1 || atoi(e) == 2)) cg = atoi(e); }
+  if (force_cg == 1 || force_cg == 2) cg = force_cg;
   p.n_queries = (int)n_queries;
   p.q_tiles = (int)((n_queries + TILE_M - 1) / TILE_M);
   p.q_tiles = (p.q_tiles + cg - 1) / cg * cg;
@@ -1279,7 +1203,7 @@ static void mma_plan(int64_t n_queries, int64_t n_rows, int sm_count, MmaParams&
   p.v_aligned = p.n_aligned == n_pairs ? p.v_tiles
                                        : (int)(((long long)p.n_aligned * p.v_tiles + n_pairs / 2) / n_pairs);
   if (p.seg == 0) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; }
-  { const char* e = getenv("MMF_MMA_FLAT"); if (e && atoi(e)) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; } }
+  if (flat) { p.seg = 1; p.n_aligned = 0; p.v_aligned = 0; }
 }
 
 // Host-only self check of the decomposition (no GPU needed): every (query-tile group, vault tile) unit must
@@ -1354,9 +1278,13 @@ template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const MmaParams& p, int n_pairs,
                       double threshold, float* out_scores, int64_t* out_rows, uint64_t* out_packed, float* out_disc,
                       cudaStream_t st) {
-  const int smem = mma_smem_bytes(SPLIT, CG, (VAR & VAR_DEEP) != 0) + 256 + 1024;
+  const int smem = mma_smem_bytes(SPLIT, CG) + 256 + 1024;
   auto kern = vault_mma_topk_kernel<SPLIT, KPL, CG, KR, VAR>;
-  MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  static unsigned long long attr_set = 0;     // per instantiation and device: the attribute sticks to the function
+  if (h->device >= 64 || !((attr_set >> h->device) & 1ull)) {
+    MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (h->device < 64) attr_set |= 1ull << h->device;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_pairs * CG));
   cfg.blockDim = dim3(MMA_THREADS);
@@ -1371,29 +1299,21 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   cfg.numAttrs = 1;
   MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
   h->launches++;
-  bool fast = true;                 // MMF_MERGE_FAST=0 selects the first form of the tails (A/B, triage)
-  { const char* e = getenv("MMF_MERGE_FAST"); if (e && atoi(e) == 0) fast = false; }
+  mmf_push_ctx no_push = {};
   if constexpr ((VAR & VAR_SCREEN) != 0) {
-    if (fast)
-      mma_rerank_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
-                                                                     (long long*)out_rows, (u64*)out_packed, out_disc);
-    else
-      mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
-                                                               (long long*)out_rows, (u64*)out_packed, out_disc);
+    mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                             (long long*)out_rows, (u64*)out_packed, out_disc);
   } else if constexpr ((VAR & VAR_GUARD) != 0) {
-    mma_merge_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
-                                                                  (u64*)out_packed, out_disc);
+    mma_merge_kernel<KPL, CG, true, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                                         (u64*)out_packed, out_disc, no_push);
+  } else if (h->push_ctx && out_packed && !out_scores && !out_rows && !out_disc) {
+    // row-sharded search over peer memory: the winners go to every rank's gather buffer from this kernel
+    mma_merge_kernel<KPL, CG, false, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, nullptr, nullptr, nullptr,
+                                                                         nullptr, *h->push_ctx);
+    h->push_fused = true;
   } else {
-    if (fast && h->push_ctx && out_packed && !out_scores && !out_rows && !out_disc) {
-      // row-sharded search with the fused push: the winners go to every rank's gather buffer from this kernel
-      mma_merge_push_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, *h->push_ctx);
-      h->push_fused = true;
-    } else if (fast)
-      mma_merge_kernel<KPL, CG, false, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores,
-                                                                          (long long*)out_rows, (u64*)out_packed, out_disc);
-    else
-      mma_merge_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
-                                                              (u64*)out_packed, out_disc);
+    mma_merge_kernel<KPL, CG, false, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+                                                                          (u64*)out_packed, out_disc, no_push);
   }
   MMF_LAUNCH_OK(h);
   return MMF_OK;
@@ -1420,35 +1340,32 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const int C = 32 * kpl;
 
   MmaParams p;
-  { const char* e = getenv("MMF_MMA_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  p.debug = h->opt.debug;
   int cg, n_pairs;
-  mma_plan(n_queries, h->vault_rows, h->sm_count, p, cg, n_pairs);
+  mma_plan(n_queries, h->vault_rows, h->sm_count, p, cg, n_pairs, h->opt.force_cg, h->opt.flat_schedule != 0);
   p.row_base = (u32)h->vault_row_offset;
   p.top_k = top_k;
   p.inv_scale = split ? (MMF_SPLIT_INV_SCALE * MMF_SPLIT_INV_SCALE) : 1.0f;
   const long long strips = (long long)n_pairs + p.qtp;
   const long long lists = strips * 2 * cg * TILE_M;
+  // fp32-exact vaults, top_k <= 16: screened search (VAR_SCREEN); option "screen" = 0 selects the 3-pass kernel
+  const bool screen = split && top_k <= 16 && h->opt.screen != 0;
+  const bool hist = top_k > 16;                   // KR == 0 variants: score histogram instead of the bucket pool
 
-  // scratch: [64 KB counters (stream kernel) | query planes | g_tau | cand_cnt | cand]
+  // scratch: [64 KB counters (stream kernel) | query planes | g_tau | pool | cand_cnt | (screened: overflow flag 1 KB |
+  //           cand_cnt of the guarded pass | its g_tau | its pool | fp32 queries) | cand]
   auto al = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   const size_t off_q = 65536;
   const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
   const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
   const size_t off_cnt = off_pool + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4);
-  const size_t off_cand = off_cnt + al((size_t)lists * 4);
-  // fp32-exact vaults, top_k <= 16: screened search (VAR_SCREEN); MMF_MMA_SCREEN=0 selects the 3-pass kernel (A/B, triage)
-  bool screen = split && top_k <= 16;
-  { const char* e = getenv("MMF_MMA_SCREEN"); if (e && atoi(e) == 0) screen = false; }
-  const size_t off_qn = off_cand + al((size_t)lists * C * 8);
-  const size_t off_flag = off_qn + (screen ? al((size_t)p.q_pad * MMF_DIM * 4) : 0);
-  bool lean = false;                  // experimental (round 2 A/B): 5-launch sequence, see mma_query_prep_lean_kernel
-  { const char* e = getenv("MMF_MMA_LEAN"); lean = screen && e && atoi(e) != 0; }
-  // lean: [flag 1 KB | cand_cnt of the guarded pass] (one contiguous region to clear) | g_tau2 | pool2
-  const size_t off_cnt2 = off_flag + 1024;
-  const size_t off_tau2 = off_cnt2 + al((size_t)lists * 4);
-  const size_t off_pool2 = off_tau2 + al((size_t)p.q_pad * 4);
-  const size_t total = lean ? off_pool2 + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4)
-                            : screen ? off_flag + 1024 : off_cand + (size_t)lists * C * 8;
+  const size_t off_flag = off_cnt + al((size_t)lists * 4);                 // contiguous with cand_cnt: cleared together
+  const size_t off_cnt2 = off_flag + (screen ? 1024 : 0);
+  const size_t off_tau2 = off_cnt2 + (screen ? al((size_t)lists * 4) : 0);
+  const size_t off_pool2 = off_tau2 + (screen ? al((size_t)p.q_pad * 4) : 0);
+  const size_t off_qn = off_pool2 + (screen ? al((size_t)p.q_pad * MMF_MAX_TOP_K * 4) : 0);
+  const size_t off_cand = off_qn + (screen ? al((size_t)p.q_pad * MMF_DIM * 4) : 0);
+  const size_t total = off_cand + (size_t)lists * C * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* sc = (char*)h->scratch();
@@ -1462,20 +1379,11 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.margin = screen ? 2.0f * SCREEN_EPS : 0.f;
   p.qn = screen ? (const float*)(sc + off_qn) : nullptr;
 
-  if (!lean) MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));   // pairs without tiles never write theirs
-  // top_k > 16 (lazy thresholds): grid-wide bound from the score histogram (VAR_HIST); MMF_MMA_BOUND=pool selects the
-  // bucket maxima of round 1 (A/B, triage)
-  bool hist = top_k > 16;
-  { const char* e = getenv("MMF_MMA_BOUND"); if (e && (e[0] == 'p' || e[0] == '0')) hist = false; }
-  if (lean) {
-    mma_query_prep_lean_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(
-        queries, p.n_queries, p.q_pad, planes, p.g_tau, p.pool, top_k, (float*)(sc + off_qn), p.cand_cnt, (long long)lists,
-        (int*)(sc + off_flag), (long long)(256 + lists), (u32*)(sc + off_tau2), (u32*)(sc + off_pool2));
-  } else {
-    if (screen) MMF_CUDA_OK(h, cudaMemsetAsync(p.ovf, 0, 4, st));
-    mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau,
-                                                             p.pool, top_k, hist ? 1 : 0, screen ? (float*)(sc + off_qn) : nullptr);
-  }
+  // ONE preparation launch: query planes, bounds, cleared counters (pairs without tiles never write theirs)
+  mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(
+      queries, p.n_queries, p.q_pad, split ? 1 : 0, planes, p.g_tau, p.pool, top_k, hist ? 1 : 0,
+      screen ? (float*)(sc + off_qn) : nullptr, p.cand_cnt, (long long)((screen ? off_tau2 : off_flag) - off_cnt) / 4,
+      screen ? (u32*)(sc + off_tau2) : nullptr, screen ? (u32*)(sc + off_pool2) : nullptr);
   MMF_LAUNCH_OK(h);
 
   CUtensorMap tm_q;
@@ -1486,51 +1394,37 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
                   strides, box))
     return mmf_set_error(h, MMF_ERR_CUDA, "cuTensorMapEncodeTiled failed for the query operand");
 
-#define MMF_MMA_CASE(SPLIT_, KPL_, KR_, HIST_)                                                                      \
-  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2, KR_, HIST_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,      \
-                                                           out_packed, out_disc, st)                                   \
-                 : launch_mma<SPLIT_, KPL_, 1, KR_, HIST_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,      \
-                                                           out_packed, out_disc, st)
+#define MMF_MMA_CASE(SPLIT_, KPL_, KR_, VAR_)                                                                       \
+  return cg == 2 ? launch_mma<SPLIT_, KPL_, 2, KR_, VAR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,       \
+                                                          out_packed, out_disc, st)                                    \
+                 : launch_mma<SPLIT_, KPL_, 1, KR_, VAR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,       \
+                                                          out_packed, out_disc, st)
+  // 1-plane kernels with the bucket pool: PARITY (warp sets alternate tiles) wins on short strips, where the warm-up
+  // of a strip weighs (C2: 105 tiles per strip, 0.293 vs 0.344 ms), all warps on every tile on long ones (4096
+  // queries x 1.25 M rows, top-10: 3.47 vs 4.15 ms); option "epi_parity": -1 = by strip length, 0 / 1 = forced
+  const long long tiles_per_strip = p.n_aligned ? p.v_aligned / p.seg : p.v_tiles;
+  const bool parity = h->opt.epi_parity < 0 ? tiles_per_strip < 1024 : h->opt.epi_parity != 0;
   if (screen) {
     // 1 pass over the hi planes + exact re-scoring of the survivors; then the guarded 3-pass search, which
-    // returns at once unless a candidate band overflowed (its bounds must restart from scratch: the
-    // screening pass published bounds on APPROXIMATE scores)
-    bool deep = false;                // experimental (round 2 A/B): MMF_MMA_STAGES=12 -> deeper shared-memory ring
-    { const char* e = getenv("MMF_MMA_STAGES"); deep = e && atoi(e) == 12 && cg == 2; }
-    bool pref = false;                // experimental (round 2 A/B): MMF_MMA_PREFETCH=1 -> L2 prefetch of the vault tiles
-    { const char* e = getenv("MMF_MMA_PREFETCH"); pref = e && atoi(e) != 0 && cg == 2; }
+    // returns at once unless a candidate band overflowed (its bounds restart from scratch -- the screening
+    // pass published bounds on APPROXIMATE scores -- and were prepared by the same launch as the first set)
 #define MMF_SCREEN_LAUNCH(CG_, VAR_) \
   launch_mma<false, 8, CG_, 16, VAR_>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows, out_packed, out_disc, st)
-    rc = (deep && pref) ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_DEEP | VAR_PREFETCH)
-         : deep         ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_DEEP)
-         : pref         ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_PREFETCH)
-         : cg == 2      ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN)
-                        : MMF_SCREEN_LAUNCH(1, VAR_SCREEN);
+    rc = cg == 2 ? (parity ? MMF_SCREEN_LAUNCH(2, VAR_SCREEN | VAR_PARITY) : MMF_SCREEN_LAUNCH(2, VAR_SCREEN))
+                 : (parity ? MMF_SCREEN_LAUNCH(1, VAR_SCREEN | VAR_PARITY) : MMF_SCREEN_LAUNCH(1, VAR_SCREEN));
 #undef MMF_SCREEN_LAUNCH
     if (rc != MMF_OK) return rc;
-    if (lean) {                       // the guarded pass has its own counters and bounds, prepared by the first kernel
-      p.cand_cnt = (int*)(sc + off_cnt2);
-      p.g_tau = (u32*)(sc + off_tau2);
-      p.pool = (u32*)(sc + off_pool2);
-    } else {
-      MMF_CUDA_OK(h, cudaMemsetAsync(p.cand_cnt, 0, (size_t)lists * 4, st));
-      mma_query_prep_kernel<<<(p.q_pad + 7) / 8, 256, 0, st>>>(queries, p.n_queries, p.q_pad, 1, planes, p.g_tau, p.pool,
-                                                               top_k, 0, nullptr);
-      MMF_LAUNCH_OK(h);
-    }
-    return cg == 2 ? launch_mma<true, 8, 2, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
-                                                           out_packed, out_disc, st)
-                   : launch_mma<true, 8, 1, 16, VAR_GUARD>(h, s, tm_q, p, n_pairs, threshold, out_scores, out_rows,
-                                                           out_packed, out_disc, st);
+    p.cand_cnt = (int*)(sc + off_cnt2);
+    p.g_tau = (u32*)(sc + off_tau2);
+    p.pool = (u32*)(sc + off_pool2);
+    MMF_MMA_CASE(true, 8, 16, VAR_GUARD | VAR_PARITY);
   }
   if (split) {
-    if (top_k <= 16) MMF_MMA_CASE(true, 8, 16, 0);
-    if (hist) { if (kpl == 8) MMF_MMA_CASE(true, 8, 0, 1); MMF_MMA_CASE(true, 16, 0, 1); }
+    if (top_k <= 16) MMF_MMA_CASE(true, 8, 16, VAR_PARITY);       // 3-pass: 6144 clk of MMA per tile, PARITY hides the hand-offs
     if (kpl == 8) MMF_MMA_CASE(true, 8, 0, 0);
     MMF_MMA_CASE(true, 16, 0, 0);
   } else {
-    if (top_k <= 16) MMF_MMA_CASE(false, 8, 16, 0);
-    if (hist) { if (kpl == 8) MMF_MMA_CASE(false, 8, 0, 1); MMF_MMA_CASE(false, 16, 0, 1); }
+    if (top_k <= 16) { if (parity) MMF_MMA_CASE(false, 8, 16, VAR_PARITY); MMF_MMA_CASE(false, 8, 16, 0); }
     if (kpl == 8) MMF_MMA_CASE(false, 8, 0, 0);
     MMF_MMA_CASE(false, 16, 0, 0);
   }

@@ -37,25 +37,6 @@ struct StreamParams {
   float* out_disc;
   double threshold;
 };
-// Parameters of the screened / guarded variants.  A separate type on purpose: growing StreamParams changes the code
-// nvcc generates for EVERY instantiation (constant-bank addressing), and the default kernels are the measured ones.
-struct StreamScreenParams : StreamParams {
-  int k_part;             // entries per (block, query) list in part_keys: top_k, or the band capacity when screening
-  float margin;           // width of the candidate band in score units (2 x error bound)
-  int* ovf;               // set to 1 when a band did not fit -> the guarded exact kernel redoes the search
-};
-template <typename P> struct is_screen_params { static constexpr bool value = false; };
-template <> struct is_screen_params<StreamScreenParams> { static constexpr bool value = true; };
-template <typename P> __device__ __forceinline__ float margin_of(const P& p) {
-  if constexpr (is_screen_params<P>::value) return p.margin; else return 0.f;
-}
-template <typename P> __device__ __forceinline__ int* ovf_of(const P& p) {
-  if constexpr (is_screen_params<P>::value) return p.ovf; else return nullptr;
-}
-template <typename P> __device__ __forceinline__ int k_part_of(const P& p) {
-  if constexpr (is_screen_params<P>::value) return p.k_part; else return p.top_k;
-}
-
 // One warp per query: q / ||q|| (misinfo_forensics.py:439) + reset of the shared threshold.
 __global__ void __launch_bounds__(256) query_prep_kernel(const float* __restrict__ q, int n_queries,
                                                          float* __restrict__ qn, u32* __restrict__ g_tau) {
@@ -86,30 +67,16 @@ __device__ __forceinline__ void unpack8(const uint4& w, float (&f)[8], bool bf16
   }
 }
 
-// VARS (fp32-exact vaults, top_k <= 16; experimental, env MMF_STREAM_SCREEN=1):
-//   STREAM_SCREEN  stream only the fp16 HI plane of every row (half of the bytes).  q.vh / 2^8 is within a proven
-//                  eps of the exact score (|q.vl| / 2^8 <= |vl| / 2^8 <= 2^-11 (1 + 2^-11) < 4.9e-4 for unit q), so
-//                  every row within 2*eps of the running k-th best is kept and the LAST block re-scores the few
-//                  survivors exactly from hi+lo (the arithmetic of the exact kernel: bit-identical results) -- the
-//                  argument of DESIGN.md section 9 with a band half as wide, applied to the batch-1 path.
-//   STREAM_GUARD   the exact kernel behind the overflow flag: runs only when a band did not fit a list.
-constexpr int STREAM_SCREEN = 1, STREAM_GUARD = 2;
-constexpr float STREAM_SCREEN_EPS = 5.2e-4f;   // 4.9e-4 (above) + fp32 accumulation of both scores (< 2e-6) + head-room
-constexpr int STREAM_BAND_PART = 64;           // band entries a block may hand to the merge per query
-
-template <int QC, bool BF16, int KPL, int VARS = 0, typename P = StreamParams>
-__global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
-  constexpr bool SCREEN = (VARS & STREAM_SCREEN) != 0, GUARD = (VARS & STREAM_GUARD) != 0;
-  static_assert(!(SCREEN && BF16), "screening applies to the fp32-exact (hi/lo) layout");
-  static_assert(VARS == 0 || is_screen_params<P>::value, "the variants take StreamScreenParams");
-  const float margin = margin_of(p);
-  int* const ovf = ovf_of(p);
-  const int k_part = k_part_of(p);
+// (A screened variant of this kernel -- hi planes only + exact re-scoring of a band, like the tcgen05 search --
+// was measured on a B200 in round 2 and deleted: 0.64 ms against 0.37 ms per query.  With one query per block the
+// kernel is bound by bytes in flight per SM, not by bytes, and the band bookkeeping cost more than the lo planes.)
+template <int QC, bool BF16, int KPL>
+__global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamParams p) {
   constexpr int U = (QC <= 2) ? 4 : 2; // rows per warp in flight at once: 16 (8) independent 128-bit loads per lane
   constexpr int SUB = 4 / U;           // sub-rounds per 32-row interval (8 warps x U rows each)
   constexpr int C = 32 * KPL;          // candidate capacity per query
   constexpr int LIMIT = C - 64;        // compaction trigger (two 32-row intervals of slack)
-  constexpr int NLD = (BF16 || SCREEN) ? 2 : 4;    // 128-bit loads per lane per row
+  constexpr int NLD = BF16 ? 2 : 4;    // 128-bit loads per lane per row
   constexpr int POOL = (QC * C > 2048) ? QC * C : 2048;   // candidate buffers, later the merge's staging area
   __shared__ u64 pool[POOL];
   u64 (*buf)[C] = reinterpret_cast<u64 (*)[C]>(pool);
@@ -119,7 +86,6 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
   __shared__ int s_last;
   __shared__ SelectSmem sel;
 
-  if (GUARD && *reinterpret_cast<volatile int*>(ovf) == 0) return;     // grid-uniform: the screened search needed no redo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int q0 = blockIdx.y * QC;
   const int nq = min(QC, p.n_queries - q0);
@@ -168,7 +134,7 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
         for (int c = 0; c < 2; ++c) {
           float f[8];
           unpack8(ld[u][c], f, BF16);
-          if (!BF16 && !SCREEN) {
+          if (!BF16) {
             float g[8];
             unpack8(ld[u][c + 2], g, false);   // lo plane
 #pragma unroll
@@ -197,7 +163,7 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
             for (int qi = 0; qi < QC; ++qi) {
               if (qi < nq) {
                 const float s = BF16 ? acc[u][qi] : acc[u][qi] * MMF_SPLIT_INV_SCALE;
-                if (!(s < (SCREEN ? tau[qi] - margin : tau[qi]))) {
+                if (!(s < tau[qi])) {
                   const int pos = atomicAdd(&cnt[qi], 1);
                   buf[qi][pos] = pack_key(s, p.row_base + (u32)(r0 + u));
                 }
@@ -214,10 +180,7 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
     if (over) {
       if (warp < nq && cnt[warp] > k) {
         float t = 0.f;
-        bool band_ovf = false;
-        const int c = SCREEN ? warp_compact_band<KPL>(buf[warp], cnt[warp], k, margin, LIMIT - 32, &t, &band_ovf)
-                             : warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
-        if (SCREEN && band_ovf && lane == 0) *ovf = 1;
+        const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
         if (lane == 0) {
           cnt[warp] = c;
           const u32 tk = okey(t);
@@ -230,11 +193,8 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
   __syncthreads();
   if (warp < nq) {
     float t;
-    bool band_ovf = false;
-    const int c = SCREEN ? warp_compact_band<KPL>(buf[warp], cnt[warp], k, margin, STREAM_BAND_PART, &t, &band_ovf)
-                         : warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
-    if (SCREEN && band_ovf && lane == 0) *ovf = 1;
-    u64* dst = p.part_keys + ((long long)blockIdx.x * p.n_queries + q0 + warp) * (SCREEN ? k_part : k);
+    const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
+    u64* dst = p.part_keys + ((long long)blockIdx.x * p.n_queries + q0 + warp) * k;
     for (int i = lane; i < c; i += 32) dst[i] = buf[warp][i];
     if (lane == 0) p.part_cnt[(long long)blockIdx.x * p.n_queries + q0 + warp] = c;
   }
@@ -248,73 +208,6 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const P p) {
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if constexpr (SCREEN) {
-    // merge of the screened search: approximate top-k of the staged band -> exact re-scoring -> exact top-k
-    for (int qi = 0; qi < nq; ++qi) {
-      const long long qg = q0 + qi;
-      CandidateLists src;
-      src.lists = p.part_keys + qg * k_part;
-      src.counts = p.part_cnt + qg;
-      src.n_lists = gridDim.x;
-      src.k_in = k_part;
-      src.list_stride = (long long)p.n_queries * k_part;
-      src.count_stride = p.n_queries;
-      const u32 g = *reinterpret_cast<volatile u32*>(p.g_tau + qg);       // bounds the k-th best APPROXIMATE score
-      const u64 min_key = g ? (u64)okey(okey_inv(g) - margin) << 32 : 0ull;
-      const u32 n = stage_candidates(src, sel, pool, POOL, min_key);
-      if (n > (u32)POOL) {                                               // band too wide to stage: exact redo
-        if (tid == 0) *ovf = 1;
-        continue;
-      }
-      CandidateLists ex;
-      ex.lists = pool; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n; ex.list_stride = 0; ex.count_stride = 0;
-      const bool by_rank = n <= (u32)RANK_SELECT_MAX;
-      if (by_rank) block_rank_select(pool, (int)n, k, sel);
-      else block_select_topk(ex, k, sel, pool, 0, 0ull, nullptr, nullptr, nullptr, nullptr, p.threshold);
-      const u64 kth = sel.win[k - 1];                                      // 0: fewer than k candidates -> keep all
-      const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - margin) << 32 : 0ull;
-      __syncthreads();
-      float qv[16];                                                        // lane's elements of the normalised query
-#pragma unroll
-      for (int e = 0; e < 16; ++e) qv[e] = p.qn[qg * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)];
-      for (u32 i = warp; i < n; i += 8) {
-        const u64 key = pool[i];
-        u64 exact = 0ull;
-        if (key >= cut) {                                                  // warp-uniform
-          const u32 row = (u32)key;
-          const uint4* rp = vault + (long long)(row - p.row_base) * ROW_U4;
-          uint4 ld[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) ld[c] = ldg_stream(rp + c * 32 + lane);
-          float a = 0.f;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            float f[8], gl[8];
-            unpack8(ld[c], f, false);
-            unpack8(ld[c + 2], gl, false);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) a = fmaf(f[e] + gl[e], qv[c * 8 + e], a);   // the exact kernel's arithmetic
-          }
-          a = warp_sum(a);
-          exact = pack_key(a * MMF_SPLIT_INV_SCALE, row);
-        }
-        __syncwarp();
-        if (lane == 0) pool[i] = exact;
-      }
-      __syncthreads();
-      float* os = p.out_scores ? p.out_scores + qg * k : nullptr;
-      long long* orow = p.out_rows ? p.out_rows + qg * k : nullptr;
-      u64* op = p.out_packed ? p.out_packed + qg * k : nullptr;
-      float* od = p.out_disc ? p.out_disc + qg : nullptr;
-      if (by_rank) {
-        block_rank_select(pool, (int)n, k, sel);
-        write_topk_outputs(sel, k, os, orow, op, od, p.threshold);
-      } else {
-        block_select_topk(ex, k, sel, pool, 0, 0ull, os, orow, op, od, p.threshold);
-      }
-    }
-    return;
-  }
   for (int qi = 0; qi < nq; ++qi) {
     const long long qg = q0 + qi;
     CandidateLists src;
@@ -380,16 +273,6 @@ static void launch_stream_q(int qc, int kpl, dim3 grid, cudaStream_t st, const S
   else launch_stream_k<8, BF16>(kpl, grid, st, p);
 }
 
-// screened batch-1 path: hi-plane pass (KPL = 8: room for the band), then the guarded exact kernel (KPL = 4: top_k <= 16)
-template <int VARS>
-static void launch_stream_screen(int qc, dim3 grid, cudaStream_t st, const StreamScreenParams& p) {
-  constexpr int KPL = (VARS & STREAM_SCREEN) ? 8 : 4;
-  if (qc == 1) vault_stream_topk_kernel<1, false, KPL, VARS, StreamScreenParams><<<grid, 256, 0, st>>>(p);
-  else if (qc == 2) vault_stream_topk_kernel<2, false, KPL, VARS, StreamScreenParams><<<grid, 256, 0, st>>>(p);
-  else if (qc == 4) vault_stream_topk_kernel<4, false, KPL, VARS, StreamScreenParams><<<grid, 256, 0, st>>>(p);
-  else vault_stream_topk_kernel<8, false, KPL, VARS, StreamScreenParams><<<grid, 256, 0, st>>>(p);
-}
-
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Streaming search over the resident shard.  Exactly one of (out_scores/out_rows) or out_packed
@@ -406,18 +289,12 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   long long rows_per_cta = align_up((size_t)((h->vault_rows + gx - 1) / gx), 32);
   gx = (h->vault_rows + rows_per_cta - 1) / rows_per_cta;
 
-  // experimental (round 2 A/B): screened batch-1 search, see STREAM_SCREEN
-  bool screen = false;
-  { const char* e = getenv("MMF_STREAM_SCREEN");
-    screen = e && atoi(e) != 0 && h->vault_mode == MMF_VAULT_FP32 && top_k <= 16 && h->vault_nan_rows == 0; }
-  const int k_part = screen ? STREAM_BAND_PART : top_k;
-  // scratch: [done 64 KB | qn | g_tau | part_cnt | part_keys | (screened: g_tau of the guarded pass, overflow flag)]
+  // scratch: [done 64 KB | qn | g_tau | part_cnt | part_keys]
   const size_t off_qn = 65536;
   const size_t off_tau = off_qn + align_up((size_t)Q * MMF_DIM * 4, 256);
   const size_t off_cnt = off_tau + align_up((size_t)Q * 4, 256);
   const size_t off_keys = off_cnt + align_up((size_t)gx * Q * 4, 256);
-  const size_t off_tau2 = off_keys + align_up((size_t)gx * Q * k_part * 8, 256);
-  const size_t total = screen ? off_tau2 + align_up((size_t)Q * 4 + 256, 256) : off_keys + (size_t)gx * Q * top_k * 8;
+  const size_t total = off_keys + (size_t)gx * Q * top_k * 8;
   int rc = mmf_ensure_scratch(h, total, st);
   if (rc != MMF_OK) return rc;
   char* s = (char*)h->scratch();
@@ -445,24 +322,6 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   p.out_disc = out_disc;
   p.threshold = threshold;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  if (screen) {
-    StreamScreenParams sp;
-    static_cast<StreamParams&>(sp) = p;
-    sp.k_part = k_part;
-    sp.margin = 2.0f * STREAM_SCREEN_EPS;
-    sp.ovf = (int*)(s + off_tau2 + (size_t)Q * 4);
-    // [g_tau of the guarded pass | flag] cleared together; hi-plane pass + exact re-scoring; then the exact kernel,
-    // which returns at once unless a band overflowed (it starts from its own zero bounds: the screening pass
-    // published bounds on APPROXIMATE scores)
-    MMF_CUDA_OK(h, cudaMemsetAsync(s + off_tau2, 0, (size_t)Q * 4 + 4, st));
-    launch_stream_screen<STREAM_SCREEN>(qc, grid, st, sp);
-    MMF_LAUNCH_OK(h);
-    sp.g_tau = (u32*)(s + off_tau2);
-    sp.k_part = top_k;
-    launch_stream_screen<STREAM_GUARD>(qc, grid, st, sp);
-    MMF_LAUNCH_OK(h);
-    return MMF_OK;
-  }
   if (h->vault_mode == MMF_VAULT_BF16) launch_stream_q<true>(qc, kpl, grid, st, p);
   else launch_stream_q<false>(qc, kpl, grid, st, p);
   MMF_LAUNCH_OK(h);
