@@ -26,3 +26,6 @@ echo "built tools/cabi_selftest"
 echo "built tools/hbm_stride_micro"
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tma_stream_micro tools/tma_stream_micro.cu
 echo "built tools/tma_stream_micro"
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o tools/shard_selftest tools/shard_selftest.cu \
+  -L"$PKG" -lmmf_b200 -lpthread -Xlinker -rpath -Xlinker "\$ORIGIN/../$PKG"
+echo "built tools/shard_selftest"

@@ -199,6 +199,24 @@ int mmf_fusion_forward(mmf_handle* h, const float* x, int64_t n, float* out_prob
 int mmf_verdict_batch(mmf_handle* h, const float* scores, const uint8_t* modality, int64_t n, float* out_probs,
                       int32_t* out_verdict, float* out_confidence, mmf_stream_t stream);
 
+/* Score assembly + verdict in ONE launch, device buffers (batched misinfo_forensics.py:794-809 + :866-900):
+ * head (n,3) = [ai, misinfo, deepfake]; modality (n) uint8 (bit0 text, bit1 visual) or NULL = both;
+ * clip_similarity / vault_discrepancy (n) are read AND masked in place (a skipped modality's score is 0);
+ * out_scores5 (n,5) = the fusion inputs; outputs as mmf_fusion_forward. */
+int mmf_verdict_assemble(mmf_handle* h, const float* head, const uint8_t* modality, int64_t n, float* clip_similarity,
+                         float* vault_discrepancy, float* out_scores5, float* out_probs, int32_t* out_verdict,
+                         float* out_confidence, mmf_stream_t stream);
+
+/* The whole path for a batch, DEVICE buffers in and out, asynchronous on `stream`: caption/image cosine, vault
+ * search of the image embeddings (zero discrepancy / NaN, -1 matches when no vault is loaded), score assembly +
+ * fusion judge / fallback verdict.  Shapes as mmf_score_batch_host; every output but verdict / confidence is
+ * required.  Single-GPU / replica vaults (row-sharded: mmf_cosine_pairs + mmf_vault_search_sharded +
+ * mmf_verdict_assemble). */
+int mmf_score_batch(mmf_handle* h, const float* text, const float* image, const float* head, const uint8_t* modality,
+                    int64_t n, int top_k, double threshold, int algo, float* out_clip_similarity,
+                    float* out_vault_discrepancy, float* out_vault_scores, int64_t* out_vault_rows, float* out_scores5,
+                    float* out_probs, int32_t* out_verdict, float* out_confidence, mmf_stream_t stream);
+
 /* The whole path for a batch with HOST buffers in and out (the end-to-end call): H2D of the embeddings,
  * caption/image cosine, vault search (zero discrepancy / no matches when no vault is loaded, misinfo_forensics.py:
  * 422-428), score assembly with the skipped-modality zeros of :794-809 + fusion judge / fallback verdict, one D2H,

@@ -47,6 +47,12 @@ SIGNATURES = {
     "mmf_fusion_forward": (_i, [_p, _p, _l, _p, _p, _p, _p]),
     "mmf_verdict_batch": (_i, [_p, _p, _p, _l, _p, _p, _p, _p]),
     "mmf_score_batch_host": (_i, [_p, _p, _p, _p, _p, _l, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mmf_verdict_assemble": (_i, [_p, _p, _p, _l, _p, _p, _p, _p, _p, _p, _p]),
+    "mmf_score_batch": (_i, [_p, _p, _p, _p, _p, _l, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mmf_score_batch_submit": (_i, [_p, _i, _p, _p, _p, _p, _l, _i, _d, _i]),
+    "mmf_score_batch_collect": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "mmf_set_option": (_i, [_p, C.c_char_p, _i]),
+    "mmf_get_option": (_i, [_p, C.c_char_p, C.POINTER(_i)]),
     "mmf_mma_plan_check": (_i, [_l, _l, _i, C.POINTER(_l), C.POINTER(_i), C.POINTER(_i)]),
     "mmf_mma_hist_bound": (_i, [_p, _l, _i, C.POINTER(C.c_float)]),
     "mmf_mma_screen_eps": (_d, []),

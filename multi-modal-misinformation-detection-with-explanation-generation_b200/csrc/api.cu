@@ -323,6 +323,42 @@ struct BatchLayout {       // byte offsets inside a slot's device buffer: inputs
 };
 }  // namespace
 
+// Score assembly + verdict for device-resident scores (the tail of the batched path as ONE launch): see the header.
+extern "C" int mmf_verdict_assemble(mmf_handle* h, const float* head, const uint8_t* modality, int64_t n, float* clip_similarity,
+                                    float* vault_discrepancy, float* out_scores5, float* out_probs, int32_t* out_verdict,
+                                    float* out_confidence, mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n < 0 || (n > 0 && (!head || !clip_similarity || !vault_discrepancy || !out_scores5 || !out_probs)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "verdict_assemble: bad argument");
+  return mmf_assemble_verdict(h, head, modality, n, clip_similarity, vault_discrepancy, out_scores5, out_probs, out_verdict,
+                              out_confidence, (cudaStream_t)stream);
+}
+
+// The whole path for a batch, DEVICE buffers in and out, asynchronous on `stream`: see the header.
+extern "C" int mmf_score_batch(mmf_handle* h, const float* text, const float* image, const float* head, const uint8_t* modality,
+                               int64_t n, int top_k, double threshold, int algo, float* out_clip_similarity,
+                               float* out_vault_discrepancy, float* out_vault_scores, int64_t* out_vault_rows, float* out_scores5,
+                               float* out_probs, int32_t* out_verdict, float* out_confidence, mmf_stream_t stream) {
+  if (!h) return MMF_ERR_BAD_ARG;
+  if (n < 0 || top_k <= 0 || top_k > MMF_MAX_TOP_K ||
+      (n > 0 && (!text || !image || !head || !out_clip_similarity || !out_vault_discrepancy || !out_vault_scores || !out_vault_rows ||
+                 !out_scores5 || !out_probs)))
+    return mmf_set_error(h, MMF_ERR_BAD_ARG, "score_batch: bad argument (n=%lld top_k=%d)", (long long)n, top_k);
+  if (!h->fusion_loaded) return mmf_set_error(h, MMF_ERR_NOT_LOADED, "score_batch: fusion weights not loaded");
+  if (n == 0) return MMF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = mmf_cosine_pairs(h, text, image, n, MMF_DIM, 0.0, out_clip_similarity, nullptr, stream);
+  if (rc != MMF_OK) return rc;
+  if (h->vault_loaded)
+    rc = search_dispatch(h, image, n, top_k, threshold, algo, out_vault_scores, out_vault_rows, nullptr, out_vault_discrepancy, st,
+                         "score_batch");
+  else
+    rc = mmf_fill_empty(h, n, top_k, out_vault_scores, out_vault_rows, nullptr, out_vault_discrepancy, st);
+  if (rc != MMF_OK) return rc;
+  return mmf_assemble_verdict(h, head, modality, n, out_clip_similarity, out_vault_discrepancy, out_scores5, out_probs, out_verdict,
+                              out_confidence, st);
+}
+
 extern "C" int mmf_score_batch_submit(mmf_handle* h, int slot, const float* text_host, const float* image_host,
                                       const float* head_host, const uint8_t* modality_host, int64_t n, int top_k,
                                       double threshold, int algo) {

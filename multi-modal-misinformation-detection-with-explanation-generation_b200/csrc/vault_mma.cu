@@ -362,9 +362,15 @@ __device__ __forceinline__ void prep_query_row(const float* __restrict__ q, int 
     ss = fmaf(v[j], v[j], ss);
   }
   const float norm = sqrtf(warp_sum(ss));
+  // q / |q| is NaN for an all-zero (or NaN) embedding: every similarity is NaN, np.argsort keeps the row order and the
+  // reference returns the top_k HIGHEST row ids with NaN similarity (misinfo_forensics.py:439-450) -- what the
+  // streaming kernel's arithmetic yields by itself.  Here such a query is marked (g_tau = the NaN key), gets zero
+  // operands, collects no candidates, and the tail kernels write that answer (nan_query_outputs).
+  const bool nan_query = w < n_queries && !(norm > 0.f) ;
+  if (lane == 0 && nan_query) g_tau[w] = 0xFFFFFFFFu;
 #pragma unroll
   for (int j = 0; j < MMF_DIM / 32; ++j) {
-    const float x = (w < n_queries) ? v[j] / norm : 0.f;
+    const float x = (w < n_queries && !nan_query) ? v[j] / norm : 0.f;
     const long long o = (long long)w * MMF_DIM + j * 32 + lane;
     if (qn) qn[o] = x;                              // screened search: fp32 copy for the exact re-scoring
     if (split) {
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
       pool2[(long long)w * MMF_MAX_TOP_K + j * 32 + lane] = (j * 32 + lane < pool_n) ? 0u : 0xFFFFFFFFu;
   }
   prep_query_row(q, n_queries, q_pad, split, planes, g_tau, pool, top_k, hist, qn);
+  if (g_tau2 && w < q_pad && lane == 0 && g_tau[w] == 0xFFFFFFFFu) g_tau2[w] = 0xFFFFFFFFu;   // (same lane wrote it)
 }
 
 // ---- the search kernel ---------------------------------------------------------------------
@@ -680,7 +687,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         cnt_out = p.cand_cnt + list;
         g_tau = p.g_tau + qt * TILE_M + m;
         pool = p.pool + (long long)(qt * TILE_M + m) * MMF_MAX_TOP_K;
-        valid_q = (qt * TILE_M + m) < p.n_queries;
+        valid_q = (qt * TILE_M + m) < p.n_queries && *reinterpret_cast<volatile u32*>(g_tau) != 0xFFFFFFFFu;   // (NaN query: see prep)
         if (KR > 0) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) pool_prev[i] = make_uint4(0, 0, 0, 0);
@@ -942,6 +949,21 @@ __device__ __forceinline__ CandidateLists lists_of_query(const MmaParams& p, int
   return src;
 }
 
+// The answer for a NaN query (see prep_query_row): the top_k highest row ids of the shard with NaN similarity,
+// discrepancy 0; slots beyond the shard size are empty.  All threads of the block call it.
+__device__ __forceinline__ void nan_query_outputs(const MmaParams& p, int qg, float* out_scores, long long* out_rows,
+                                                  u64* out_packed, float* out_disc) {
+  for (int i = threadIdx.x; i < p.top_k; i += blockDim.x) {
+    const bool have = i < p.n_rows;
+    const u32 row = p.row_base + (u32)(p.n_rows - 1 - i);
+    const long long o = (long long)qg * p.top_k + i;
+    if (out_packed) out_packed[o] = have ? ((0xFFFFFFFFull << 32) | row) : 0ull;
+    if (out_scores) out_scores[o] = __int_as_float(0x7FC00000);
+    if (out_rows) out_rows[o] = have ? (long long)row : -1ll;
+  }
+  if (threadIdx.x == 0 && out_disc) out_disc[qg] = 0.f;
+}
+
 // Best published lower bound (score key) of query qg's top_k-th best: g_tau, and for top_k <= 16 (bucket-pool kernels)
 // the minimum over the 16 bucket maxima -- 16 distinct rows score at least that.  0 = no bound.
 __device__ __forceinline__ u32 published_bound(const MmaParams& p, int qg) {
@@ -985,10 +1007,17 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   __shared__ bool last;
   if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
   const int qg = blockIdx.x;
-  const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
-  const u64 min_key = (u64)published_bound(p, qg) << 32;
-  const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
-  select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
+  if (p.g_tau[qg] == 0xFFFFFFFFu) {                  // NaN query (block-uniform): the top_k highest row ids, NaN keys
+    if (!PUSH) { nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc); return; }
+    for (int i = threadIdx.x; i < p.top_k; i += blockDim.x)
+      sel.win[i] = i < p.n_rows ? ((0xFFFFFFFFull << 32) | (p.row_base + (u32)(p.n_rows - 1 - i))) : 0ull;
+    __syncthreads();
+  } else {
+    const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
+    const u64 min_key = (u64)published_bound(p, qg) << 32;
+    const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
+    select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
+  }
   if (!PUSH) {
     write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                        out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
@@ -1042,6 +1071,7 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   __shared__ int n_slots;
   const int qg = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p.g_tau[qg] == 0xFFFFFFFFu) { nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc); return; }
   // bounds on the k-th best APPROXIMATE score; candidates down to margin below it may matter
   const u32 g = published_bound(p, qg);
   const u64 min_key = g ? (u64)okey(okey_inv(g) - p.margin) << 32 : 0ull;

@@ -43,6 +43,7 @@ class Engine:
         self.vault_rows = 0
         self.vault_row_offset = 0
         self.vault_mode = None
+        self._pending = {}          # slot -> host arrays of a submitted batch (kept alive until collected)
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
@@ -166,30 +167,150 @@ class Engine:
                                             _ptr(scores), _ptr(rows), _ptr(disc), self._stream()))
         return scores, rows, disc
 
+    def verdict_assemble(self, head_scores, modality, clip_similarity: torch.Tensor, vault_discrepancy: torch.Tensor):
+        """Score assembly (skipped modalities zeroed) + fusion judge / fallback verdict in one launch.  clip_similarity
+        and vault_discrepancy are device fp32 tensors, masked IN PLACE.  Returns (scores5, probs, verdict, confidence)."""
+        hs = self._dev_f32(head_scores, 3)
+        n = hs.shape[0]
+        mod = None if modality is None else torch.as_tensor(modality).to(device=self.device, dtype=torch.uint8).contiguous()
+        x = torch.empty((n, 5), dtype=torch.float32, device=self.device)
+        probs = torch.empty((n, 2), dtype=torch.float32, device=self.device)
+        verdict = torch.empty(n, dtype=torch.int32, device=self.device)
+        conf = torch.empty(n, dtype=torch.float32, device=self.device)
+        self._check(self.lib.mmf_verdict_assemble(self._h, _ptr(hs), _ptr(mod), n, _ptr(clip_similarity), _ptr(vault_discrepancy),
+                                                  _ptr(x), _ptr(probs), _ptr(verdict), _ptr(conf), self._stream()))
+        return x, probs, verdict, conf
+
+    def score_batch(self, text_embeds, image_embeds, head_scores, modality=None, top_k: int = 5,
+                    threshold: float = VAULT_THRESHOLD, algo: str = "auto") -> dict:
+        """The whole hot path for a batch in ONE asynchronous library call on device tensors (host tensors are copied
+        in first): dict of device tensors, keys as score_batch_host.  Uses the vault resident in this engine (none:
+        zero discrepancy, no matches)."""
+        t, im, hs = self._dev_f32(text_embeds, 512), self._dev_f32(image_embeds, 512), self._dev_f32(head_scores, 3)
+        n = im.shape[0]
+        if t.shape[0] != n or hs.shape[0] != n:
+            raise ValueError("score_batch: text / image / head batch sizes differ")
+        mod = None if modality is None else torch.as_tensor(modality).to(device=self.device, dtype=torch.uint8).contiguous()
+        dev = self.device
+        out = {"clip_similarity": torch.empty(n, dtype=torch.float32, device=dev), "vault_discrepancy": torch.empty(n, dtype=torch.float32, device=dev),
+               "vault_scores": torch.empty((n, top_k), dtype=torch.float32, device=dev), "vault_rows": torch.empty((n, top_k), dtype=torch.int64, device=dev),
+               "scores": torch.empty((n, 5), dtype=torch.float32, device=dev), "probs": torch.empty((n, 2), dtype=torch.float32, device=dev),
+               "verdict": torch.empty(n, dtype=torch.int32, device=dev), "confidence": torch.empty(n, dtype=torch.float32, device=dev)}
+        self._check(self.lib.mmf_score_batch(self._h, _ptr(t), _ptr(im), _ptr(hs), _ptr(mod), n, int(top_k), float(threshold), _ALGO[algo],
+                                             *[_ptr(out[k]) for k in self._BATCH_KEYS], self._stream()))
+        return out
+
+    _BATCH_KEYS = ("clip_similarity", "vault_discrepancy", "vault_scores", "vault_rows", "scores", "probs", "verdict", "confidence")
+
+    @staticmethod
+    def _host(x, cols, dt):
+        a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)   # a CPU tensor is not copied
+        return np.ascontiguousarray(a, dtype=dt).reshape(-1, cols) if cols else np.ascontiguousarray(a, dtype=dt).reshape(-1)
+
+    def score_batch_submit(self, slot: int, text_embeds, image_embeds, head_scores, modality=None, top_k: int = 5,
+                           threshold: float = VAULT_THRESHOLD, algo: str = "auto") -> None:
+        """Enqueue the whole hot path for one batch with host buffers (mmf_score_batch_submit): H2D, kernels and D2H run
+        on the library's own streams, the call returns at once.  Two slots (0, 1): submit batch i+1 before collecting
+        batch i and the copies of one overlap the kernels of the other.  The input arrays are kept alive until the
+        slot is collected."""
+        t, im, hs = self._host(text_embeds, 512, np.float32), self._host(image_embeds, 512, np.float32), self._host(head_scores, 3, np.float32)
+        n = im.shape[0]
+        if t.shape[0] != n or hs.shape[0] != n:
+            raise ValueError("score_batch: text / image / head batch sizes differ")
+        mod = None if modality is None else self._host(modality, 0, np.uint8)
+        self._check(self.lib.mmf_score_batch_submit(self._h, int(slot), t.ctypes.data, im.ctypes.data, hs.ctypes.data,
+                                                    None if mod is None else mod.ctypes.data, n, int(top_k), float(threshold), _ALGO[algo]))
+        self._pending[int(slot)] = (t, im, hs, mod, n, int(top_k))
+
+    def score_batch_collect(self, slot: int) -> dict:
+        """Wait for the batch submitted in `slot` and return its results as numpy arrays (keys as score_batch_host)."""
+        if int(slot) not in self._pending:
+            raise MMFError(_lib.ERR_BAD_ARG, f"score_batch_collect: nothing submitted in slot {slot}")
+        *_, n, top_k = self._pending.pop(int(slot))
+        out = {"clip_similarity": np.empty(n, np.float32), "vault_discrepancy": np.empty(n, np.float32),
+               "vault_scores": np.empty((n, top_k), np.float32), "vault_rows": np.empty((n, top_k), np.int64),
+               "scores": np.empty((n, 5), np.float32), "probs": np.empty((n, 2), np.float32),
+               "verdict": np.empty(n, np.int32), "confidence": np.empty(n, np.float32)}
+        self._check(self.lib.mmf_score_batch_collect(self._h, int(slot), *[out[k].ctypes.data for k in self._BATCH_KEYS]))
+        return out
+
     def score_batch_host(self, text_embeds, image_embeds, head_scores, modality=None, top_k: int = 5,
                          threshold: float = VAULT_THRESHOLD, algo: str = "auto"):
         """The whole hot path for a batch in ONE library call with host buffers: (B,512) text / image embeddings
         and (B,3) head scores as numpy arrays or CPU tensors (pinned memory makes the copies asynchronous DMA),
         results as numpy arrays in host memory -- one D2H and one synchronisation instead of one per tensor.
         Same values as mmf_b200.score_batch.  Needs the fusion weights; a vault is optional."""
-        def host(x, cols, dt):
-            a = x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)   # a CPU tensor is not copied
-            a = np.ascontiguousarray(a, dtype=dt).reshape(-1, cols) if cols else np.ascontiguousarray(a, dtype=dt).reshape(-1)
-            return a
-        t, im, hs = host(text_embeds, 512, np.float32), host(image_embeds, 512, np.float32), host(head_scores, 3, np.float32)
-        n = im.shape[0]
-        if t.shape[0] != n or hs.shape[0] != n:
-            raise ValueError("score_batch_host: text / image / head batch sizes differ")
-        mod = None if modality is None else host(modality, 0, np.uint8)
-        out = {"clip_similarity": np.empty(n, np.float32), "vault_discrepancy": np.empty(n, np.float32),
-               "vault_scores": np.empty((n, top_k), np.float32), "vault_rows": np.empty((n, top_k), np.int64),
-               "scores": np.empty((n, 5), np.float32), "probs": np.empty((n, 2), np.float32),
-               "verdict": np.empty(n, np.int32), "confidence": np.empty(n, np.float32)}
-        self._check(self.lib.mmf_score_batch_host(
-            self._h, t.ctypes.data, im.ctypes.data, hs.ctypes.data, None if mod is None else mod.ctypes.data, n, int(top_k),
-            float(threshold), _ALGO[algo], *[out[k].ctypes.data for k in ("clip_similarity", "vault_discrepancy", "vault_scores",
-                                                                           "vault_rows", "scores", "probs", "verdict", "confidence")]))
+        self.score_batch_submit(0, text_embeds, image_embeds, head_scores, modality, top_k, threshold, algo)
+        return self.score_batch_collect(0)
+
+    def score_stream(self, batches, top_k: int = 5, threshold: float = VAULT_THRESHOLD, algo: str = "auto"):
+        """Generator over an iterable of (text, image, head[, modality]) host batches: keeps two batches in flight
+        (the copies of one overlap the kernels of the other) and yields one result dict per batch, in order."""
+        it, slot, pending = iter(batches), 0, []
+        for b in it:
+            self.score_batch_submit(slot, *b, top_k=top_k, threshold=threshold, algo=algo)
+            pending.append(slot)
+            slot ^= 1
+            if len(pending) == 2:
+                yield self.score_batch_collect(pending.pop(0))
+        while pending:
+            yield self.score_batch_collect(pending.pop(0))
+
+    # ------------------------------------------------------------------ switches (A/B, triage)
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self.lib.mmf_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int()
+        self._check(self.lib.mmf_get_option(self._h, name.encode(), C.byref(v)))
+        return int(v.value)
+
+    # ------------------------------------------------------------------ row-sharded search, library-owned NCCL (csrc/shard.cu)
+    def shard_unique_id(self) -> bytes:
+        """128 bytes that rank 0 hands to its peers (any out-of-band channel) before shard_init."""
+        buf = C.create_string_buffer(_lib.SHARD_ID_BYTES)
+        rc = self.lib.mmf_shard_unique_id(buf)
+        if rc != _lib.OK:
+            raise MMFError(rc, "mmf_shard_unique_id: NCCL library not found (set MMF_NCCL_LIB)")
+        return buf.raw
+
+    def shard_init(self, rank: int, world: int, unique_id: Optional[bytes] = None) -> None:
+        """Collective: every rank of the shard group calls this with rank 0's unique id (world == 1 needs none)."""
+        if world > 1 and (unique_id is None or len(unique_id) != _lib.SHARD_ID_BYTES):
+            raise ValueError("shard_init: unique_id must be the %d bytes of rank 0's shard_unique_id()" % _lib.SHARD_ID_BYTES)
+        self._check(self.lib.mmf_shard_init(self._h, int(rank), int(world), unique_id))
+
+    def shard_finalize(self) -> None:
+        self._check(self.lib.mmf_shard_finalize(self._h))
+
+    def shard_info(self) -> Tuple[int, int, int]:
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.mmf_shard_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return int(r.value), int(w.value), int(v.value)
+
+    def vault_search_sharded(self, queries, top_k: int = 5, threshold: float = VAULT_THRESHOLD, algo: str = "auto"
+                             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """vault_search over ALL shards of the group: local search + ONE ncclAllGather of the packed candidates +
+        merge, all inside the library on the current stream.  Same outputs on every rank."""
+        q = self._dev_f32(queries, 512)
+        nq = q.shape[0]
+        scores = torch.empty((nq, top_k), dtype=torch.float32, device=self.device)
+        rows = torch.empty((nq, top_k), dtype=torch.int64, device=self.device)
+        disc = torch.empty(nq, dtype=torch.float32, device=self.device)
+        self._check(self.lib.mmf_vault_search_sharded(self._h, _ptr(q), nq, int(top_k), float(threshold), _ALGO[algo],
+                                                      _ptr(scores), _ptr(rows), _ptr(disc), self._stream()))
+        return scores, rows, disc
+
+    def shard_all_gather(self, packed: torch.Tensor, world: int) -> torch.Tensor:
+        """The collective alone (for callers that time the phases): (Q,k) packed candidates -> (world, Q, k)."""
+        p = packed.contiguous()
+        out = torch.empty((world,) + tuple(p.shape), dtype=p.dtype, device=self.device)
+        self._check(self.lib.mmf_shard_all_gather(self._h, _ptr(p), p.numel(), _ptr(out), self._stream()))
         return out
+
+    @property
+    def collective_count(self) -> int:
+        return int(self.lib.mmf_collective_count(self._h))
 
     # ------------------------------------------------------------------ peer-memory candidate exchange
     def exchange_layout(self, world: int, n_queries: int, k_in: int) -> int:

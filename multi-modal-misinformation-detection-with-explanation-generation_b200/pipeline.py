@@ -14,11 +14,19 @@ def score_batch(engine: Engine, vault, text_embeds, image_embeds, head_scores, m
     device; host tensors are copied in, pinned memory makes that asynchronous), modality (B,)
     uint8 (bit0 text, bit1 visual; default both), vault: a TruthVault or None.
     Per row the results equal the scalar path (MisinfoForensics.analyze) on the same producer
-    outputs.  Returns a dict of device tensors."""
+    outputs.  Returns a dict of device tensors.
+
+    No torch arithmetic: a vault resident in `engine` (or none) is ONE library call (mmf_score_batch); a row-sharded
+    vault is three (cosine, sharded search with its all-gather, score assembly + verdict)."""
+    sharded = vault is not None and getattr(vault, "world", 1) > 1
+    one_call = hasattr(engine, "score_batch") and not sharded and (
+        (vault is not None and getattr(vault, "engine", None) is engine) or
+        (vault is None and not getattr(engine, "vault_rows", 0)))        # (an engine may hold a vault the caller did not pass)
+    if one_call:
+        return engine.score_batch(text_embeds, image_embeds, head_scores, modality, top_k, VAULT_THRESHOLD, algo)
     dev = engine.device
     t = torch.as_tensor(text_embeds).to(dev, torch.float32, non_blocking=True)
     im = torch.as_tensor(image_embeds).to(dev, torch.float32, non_blocking=True)
-    hs = torch.as_tensor(head_scores).to(dev, torch.float32, non_blocking=True)
     b = im.shape[0]
     sim = engine.cosine_pairs(t, im)
     if vault is not None:
@@ -27,6 +35,12 @@ def score_batch(engine: Engine, vault, text_embeds, image_embeds, head_scores, m
         vs = torch.full((b, top_k), float("nan"), device=dev)
         vr = torch.full((b, top_k), -1, dtype=torch.int64, device=dev)
         disc = torch.zeros(b, device=dev)
+    if hasattr(engine, "verdict_assemble"):
+        x, probs, verdict, conf = engine.verdict_assemble(head_scores, modality, sim, disc)
+        return {"clip_similarity": sim, "vault_discrepancy": disc, "vault_scores": vs, "vault_rows": vr,
+                "scores": x, "probs": probs, "verdict": verdict, "confidence": conf}
+    # engines without the fused tail (the CPU test double of tests/cpu_engine.py): same rules, tensor by tensor
+    hs = torch.as_tensor(head_scores).to(dev, torch.float32, non_blocking=True)
     if modality is None:
         mod = torch.full((b,), 3, dtype=torch.uint8, device=dev)
         x = torch.cat([hs, sim[:, None], disc[:, None]], dim=1)

@@ -59,9 +59,9 @@ class ShardPlan:
 
 
 def exchange_candidates(local_packed: torch.Tensor, group=None) -> torch.Tensor:
-    """The path's ONE collective: all-gather of the per-shard packed top-k candidates
-    ((Q,k) int64 each) -> (world, Q, k).  NCCL over NVLink on the GPU box; the same call
-    runs over gloo in the CPU tests of the host logic."""
+    """All-gather of the per-shard packed top-k candidates ((Q,k) int64 each) -> (world, Q, k) through
+    torch.distributed (exchange="torch"): the path the CPU tests run over gloo.  On the GPU box the default is the
+    same collective owned by the library (exchange="nccl": csrc/shard.cu, no torch in the data path)."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     nq, k = local_packed.shape
@@ -76,14 +76,20 @@ class TruthVault:
     def __init__(self, engine: Engine, embeddings, metadata: Optional[Sequence[dict]] = None, mode: str = "fp32",
                  rank: int = 0, world: int = 1, group=None, n_total: Optional[int] = None, row_offset: Optional[int] = None,
                  exchange: Optional[str] = None):
-        """exchange: how the shards' candidates meet when world > 1 -- "nccl" (one all-gather, the default) or
-        "p2p" (stores into the peers' symmetric memory + flag wait fused into the merge kernel, csrc/exchange.cu;
-        not yet validated on a multi-GPU box); None reads MMF_EXCHANGE."""
+        """exchange: how the shards' candidates meet when world > 1 --
+        "nccl"  (default) the library's own communicator: local search + ncclAllGather + merge inside
+                mmf_vault_search_sharded (csrc/shard.cu); torch.distributed only carries the 128-byte unique id once;
+        "p2p"   stores into the peers' symmetric memory + flag wait fused into the merge kernel (csrc/exchange.cu),
+                no library collective at all;
+        "torch" torch.distributed.all_gather_into_tensor between two library calls (works over gloo: the CPU tests).
+        None reads MMF_EXCHANGE, else "nccl" ("torch" for engines without the sharded entry points)."""
         self.engine = engine
-        self.exchange = (exchange or os.environ.get("MMF_EXCHANGE", "nccl")).lower()
-        if self.exchange not in ("nccl", "p2p"):
-            raise ValueError(f"exchange must be 'nccl' or 'p2p', got {self.exchange!r}")
+        default = "nccl" if hasattr(engine, "vault_search_sharded") else "torch"
+        self.exchange = (exchange or os.environ.get("MMF_EXCHANGE", default)).lower()
+        if self.exchange not in ("nccl", "p2p", "torch"):
+            raise ValueError(f"exchange must be 'nccl', 'p2p' or 'torch', got {self.exchange!r}")
         self._symm = None          # (tensor, handle, bytes) of the symmetric exchange buffer
+        self._shard_ready = False
         self.metadata = metadata
         self.mode = mode
         self.rank, self.world, self.group = rank, world, group
@@ -102,10 +108,26 @@ class TruthVault:
         self.row_offset = lo
         engine.vault_load(shard, mode=mode, row_offset=lo)
 
+    def _ensure_shard_group(self) -> None:
+        """Collective, once: rank 0's ncclUniqueId travels through torch.distributed, then every rank joins the
+        library's communicator (mmf_shard_init)."""
+        if self._shard_ready:
+            return
+        import torch.distributed as dist
+        box = [self.engine.shard_unique_id() if self.rank == 0 else None]
+        group = self.group if self.group is not None else dist.group.WORLD
+        src = dist.get_global_rank(group, 0) if hasattr(dist, "get_global_rank") else 0
+        dist.broadcast_object_list(box, src=src, group=self.group)
+        self.engine.shard_init(self.rank, self.world, box[0])
+        self._shard_ready = True
+
     def search(self, queries, top_k: int = 5, threshold: float = VAULT_THRESHOLD, algo: str = "auto"):
         """(scores (Q,k), rows (Q,k), discrepancy (Q,)) device tensors; global over all shards."""
         if self.world == 1:
             return self.engine.vault_search(queries, top_k, threshold, algo)
+        if self.exchange == "nccl":
+            self._ensure_shard_group()
+            return self.engine.vault_search_sharded(queries, top_k, threshold, algo)
         k_local = min(top_k, max(1, self.plan.rows_per_rank))
         if self.exchange == "p2p":
             nq = int(queries.shape[0]) if hasattr(queries, "shape") and len(queries.shape) == 2 else 1

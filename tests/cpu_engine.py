@@ -100,13 +100,57 @@ class OracleEngine:
         disc = np.where(flat[:, 0] != 0, oracle.discrepancy_rule(np.nan_to_num(scores[:, 0], nan=0.0), threshold), 0).astype(np.float32)
         return torch.from_numpy(scores), torch.from_numpy(rows), torch.from_numpy(disc)
 
-    # ---- the one-call host entry (Engine.score_batch_host): same dict, numpy values
+    # ---- the fused tail and the one-call entries (Engine.verdict_assemble / score_batch / score_batch_host / submit+collect)
+    def verdict_assemble(self, head_scores, modality, clip_similarity, vault_discrepancy):
+        hs = torch.as_tensor(head_scores).detach().to("cpu", torch.float32).reshape(-1, 3)
+        n = hs.shape[0]
+        mod = torch.full((n,), 3, dtype=torch.uint8) if modality is None else torch.as_tensor(modality).to(torch.uint8)
+        has_text, has_vis = (mod & 1).bool(), (mod & 2).bool()
+        zero = torch.zeros(n)
+        clip_similarity.copy_(torch.where(has_text & has_vis, clip_similarity, zero))      # masked in place, like the kernel
+        vault_discrepancy.copy_(torch.where(has_vis, vault_discrepancy, zero))
+        x = torch.stack([torch.where(has_text, hs[:, 0], zero), torch.where(has_text, hs[:, 1], zero),
+                         torch.where(has_vis, hs[:, 2], zero), clip_similarity, vault_discrepancy], dim=1)
+        probs, verdict, conf = self.verdict_batch(x, mod)
+        return x, probs, verdict, conf
+
+    def score_batch(self, text_embeds, image_embeds, head_scores, modality=None, top_k=5, threshold=oracle.VAULT_THRESHOLD, algo="auto"):
+        sim = self.cosine_pairs(text_embeds, image_embeds)
+        n = sim.shape[0]
+        if self._vault is not None:
+            vs, vr, disc = self.vault_search(image_embeds, top_k, threshold, algo)
+        else:
+            vs, vr, disc = torch.full((n, top_k), float("nan")), torch.full((n, top_k), -1, dtype=torch.int64), torch.zeros(n)
+        x, probs, verdict, conf = self.verdict_assemble(head_scores, modality, sim, disc)
+        return {"clip_similarity": sim, "vault_discrepancy": disc, "vault_scores": vs, "vault_rows": vr, "scores": x,
+                "probs": probs, "verdict": verdict, "confidence": conf}
+
     def score_batch_host(self, text_embeds, image_embeds, head_scores, modality=None, top_k=5,
                          threshold=oracle.VAULT_THRESHOLD, algo="auto"):
-        import types
-
-        import mmf_b200
-        vault = types.SimpleNamespace(search=lambda q, k, thr, a: self.vault_search(q, k, thr, a)) if self._vault is not None else None
-        out = mmf_b200.score_batch(self, vault, torch.as_tensor(text_embeds), torch.as_tensor(image_embeds),
-                                   torch.as_tensor(head_scores), modality, top_k, algo)
+        out = self.score_batch(torch.as_tensor(text_embeds), torch.as_tensor(image_embeds), torch.as_tensor(head_scores),
+                               modality, top_k, threshold, algo)
         return {k: v.numpy() for k, v in out.items()}
+
+    def score_batch_submit(self, slot, *a, **k):
+        if not hasattr(self, "_slots"):
+            self._slots = {}
+        if slot in self._slots:
+            raise RuntimeError(f"slot {slot} has not been collected")
+        self._slots[slot] = self.score_batch_host(*a, **k)
+
+    def score_batch_collect(self, slot):
+        return self._slots.pop(slot)
+
+    def vault_search_host(self, queries, top_k=5, threshold=oracle.VAULT_THRESHOLD, algo="auto"):
+        return tuple(t.numpy() for t in self.vault_search(torch.as_tensor(queries), top_k, threshold, algo))
+
+    def get_option(self, name):
+        return {"screen": 1}.get(name, 0)
+
+    def set_option(self, name, value):
+        pass
+
+    def close(self):
+        pass
+
+    collective_count = 0

@@ -53,7 +53,7 @@ def _load_bench(monkeypatch):
     spec.loader.exec_module(bench)
     cpu = torch.device("cpu")
     fake_cuda = types.SimpleNamespace(set_device=lambda *a, **k: None, synchronize=lambda *a, **k: None, Event=_Event,
-                                      is_available=lambda: False)
+                                      is_available=lambda: False, empty_cache=lambda: None)
     real_randn, real_generator = torch.randn, torch.Generator
 
     class _TorchProxy:
@@ -93,36 +93,56 @@ def _run(bench, monkeypatch, capsys, argv):
 
 
 BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-             "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"}
+             "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "records"}
 
 
-@pytest.mark.parametrize("workload", ["c2", "c3", "c4"])
+def _check_roofline(r, bound):
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source", "kernel_ms"} <= set(r)
+    assert r["bound"] == bound and r["unit"] == ("TFLOP/s" if bound == "tensor" else "GB/s")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is None        # --rows override: no ncu traffic claimed
+
+
+@pytest.mark.parametrize("workload", ["c2", "c3", "c4", "c1"])
 def test_bench_line_is_well_formed(monkeypatch, capsys, workload):
     bench = _load_bench(monkeypatch)
-    rows = {"c2": 3000, "c3": 3000, "c4": 2500}[workload]
-    if workload == "c3":                                  # keep the 1000-query latency sweep cheap on the CPU
-        real_search = OracleEngine.vault_search
-        monkeypatch.setattr(_CountingEngine, "vault_search", lambda self, q, *a, **k: real_search(self, q, *a, **k))
-    d = _run(bench, monkeypatch, capsys, ["--workload", workload, "--rows", str(rows), "--steps", "2", "--warmup", "3"])
+    rows = {"c1": 2000, "c2": 3000, "c3": 3000, "c4": 2500}[workload]
+    d = _run(bench, monkeypatch, capsys, ["--workload", workload, "--rows", str(rows), "--steps", "2", "--warmup", "3", "--records", "none"])
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
     assert d["metric"] == "vault queries/s" and d["unit"] == "queries/s" and d["higher_is_better"] is True and d["n_gpus"] == 1
     assert d["steps"] == 2 and d["warmup"] == 3 and d["value"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
     assert d["scaling"] == ("strong" if workload == "c4" else "weak") and d["dtype"] == ("bf16" if workload == "c4" else "f32")
     assert set(d["config"]) >= {"workload", "queries_per_step", "vault_rows_total", "vault_rows_per_gpu", "top_k", "parallelism", "l2"}
-    r = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r)
-    assert r["bound"] == ("tensor" if workload == "c4" else "hbm") and r["unit"] == ("TFLOP/s" if workload == "c4" else "GB/s")
-    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] is None        # --rows override: no ncu traffic claimed
-    c = d["cpu_baseline"]
-    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c and "host" in c and "batched_restatement" in c
+    _check_roofline(d["roofline"], "tensor" if workload == "c4" else "hbm")
+    assert d["records"] == {} and {"median", "min", "max"} <= set(d["step_ms_stats"])
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == "queries/s"
     assert d["gpu_launches"] > 0 and "reasons" in d["clocks"]
+    if workload == "c4":
+        assert d["cpu_baseline"] is None and {"local_search", "all_gather_us", "merge_us"} <= set(d["phases_ms"])
+        assert d["bit_exact_vs_unsharded"] is None                       # one rank: nothing to compare against
+    else:
+        c = d["cpu_baseline"]
+        assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c and "host" in c and "batched_restatement" in c
+        assert "sync_call" in e and "score_batch_submit" in e["api"]
     if workload == "c2":
+        r = d["roofline"]
         assert r["variant"].startswith("screened") and r["mma_passes"] == 1 and r["bytes_streamed_per_launch"] == rows * 512 * 2
+        assert e["d2h_bytes_per_step"] == 256 * (4 + 2 * 4 + 10 * 4 + 10 * 8 + 4 + 4 + 5 * 4 + 4)      # verdict, probs, top-10 scores / rows, sim, disc, x, conf
     if workload == "c3":
         lat = d["latency"]
-        assert lat["queries"] == 1000 and lat["p50"] <= lat["p90"] <= lat["p99"] <= lat["max"]
+        assert lat["queries"] == 1000 and lat["p50"] <= lat["p90"] <= lat["p99"] <= lat["max"] and "host_call" in lat
+
+
+def test_bench_default_run_carries_the_records(monkeypatch, capsys):
+    """what the driver runs (`bench.py --gpus 1 --steps K --warmup W`): the c2 headline plus the c1 / c3 / c4 / kernels records"""
+    bench = _load_bench(monkeypatch)
+    monkeypatch.setattr(bench, "run_kernels", lambda ctx, eng: {"cosine_pairs": [], "fusion_judge": []})   # 1M-pair sweeps: GPU-sized
+    d = _run(bench, monkeypatch, capsys, ["--rows", "2000", "--steps", "2", "--warmup", "3", "--no-cpu-baseline"])
+    assert d["cpu_baseline"] is None and set(d["records"]) == {"c1", "c3", "c4", "kernels"}
+    for name, rec in d["records"].items():
+        assert "error" not in rec, (name, rec)
+    assert d["records"]["c4"]["config"]["top_k"] == 100 and d["records"]["c4"]["roofline"]["bound"] == "tensor"
+    assert d["records"]["c3"]["latency"]["queries"] == 1000 and d["records"]["c1"]["config"]["queries_per_step"] == 1000
 
 
 def test_bench_reference_arm_line(monkeypatch, capsys):
@@ -132,14 +152,6 @@ def test_bench_reference_arm_line(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert set(d["config"]) >= {"workload", "queries_per_step", "vault_rows_total", "top_k", "parallelism"}
-
-
-def test_bench_e2e_host_api_branch(monkeypatch, capsys):
-    """--e2e-api host: the single-call host entry (not yet run on a GPU) is at least wired correctly in the harness"""
-    bench = _load_bench(monkeypatch)
-    d = _run(bench, monkeypatch, capsys, ["--rows", "3000", "--steps", "2", "--warmup", "3", "--e2e-api", "host", "--no-cpu-baseline"])
-    assert d["cpu_baseline"] is None and d["e2e"]["value"] > 0 and "score_batch_host" in d["e2e"]["api"]
-    assert d["e2e"]["d2h_bytes_per_step"] == 256 * (4 + 2 * 4 + 10 * 4 + 10 * 8 + 4 + 4 + 5 * 4 + 4)      # verdict, probs, top-10 scores / rows, sim, disc, x, conf
 
 
 def test_graft_entry_smoke_logic(monkeypatch, capsys):

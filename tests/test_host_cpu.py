@@ -326,17 +326,24 @@ def test_every_entry_point_rejects_a_null_handle():
         "mmf_score_batch_host": (N, N, N, N, N, 0, 5, 0.85, 0, N, N, N, N, N, N, N, N),
         "mmf_exchange_attach": (N, 0, 1, N, 0), "mmf_vault_search_push": (N, N, 0, 5, 0, N),
         "mmf_vault_exchange_merge": (N, 5, 0.85, N, N, N, N), "mmf_vault_search_exchange": (N, N, 0, 5, 5, 0.85, 0, N, N, N, N),
+        "mmf_score_batch_submit": (N, 0, N, N, N, N, 0, 5, 0.85, 0), "mmf_score_batch_collect": (N, 0, N, N, N, N, N, N, N, N),
+        "mmf_set_option": (N, b"screen", 1), "mmf_get_option": (N, b"screen", N),
+        "mmf_shard_init": (N, 0, 1, N), "mmf_shard_info": (N, N, N, N), "mmf_vault_search_sharded": (N, N, 0, 5, 0.85, 0, N, N, N, N),
+        "mmf_shard_all_gather": (N, N, 0, N, N),
+        "mmf_verdict_assemble": (N, N, N, 0, N, N, N, N, N, N, N),
+        "mmf_score_batch": (N, N, N, N, N, 0, 5, 0.85, 0, N, N, N, N, N, N, N, N, N),
     }
     for name, args in bad_arg.items():
         assert getattr(lib, name)(*args) == _lib.ERR_BAD_ARG, name
     assert lib.mmf_destroy(None) == 0 and lib.mmf_exchange_detach(None) == 0 and lib.mmf_launch_count(None) == 0
+    assert lib.mmf_shard_finalize(None) == 0 and lib.mmf_collective_count(None) == 0 and lib.mmf_shard_unique_id(None) == _lib.ERR_BAD_ARG
     assert lib.mmf_last_error(None) == b"null handle"
     handle_free = {"mmf_version", "mmf_arch", "mmf_status_string", "mmf_create", "mmf_mma_plan_check", "mmf_mma_hist_bound",
                    "mmf_mma_screen_eps", "mmf_exchange_layout", "mmf_destroy", "mmf_exchange_detach", "mmf_launch_count",
-                   "mmf_last_error"}
+                   "mmf_last_error", "mmf_shard_finalize", "mmf_collective_count", "mmf_shard_unique_id"}
     assert set(bad_arg) | handle_free == set(_lib.SIGNATURES)            # nothing left unchecked
     for code, text in ((0, b"ok"), (-1, b"bad argument"), (-2, b"CUDA error"), (-4, b"no CUDA device"), (-5, b"unsupported"),
-                       (-6, b"out of device memory"), (-99, b"unknown status")):
+                       (-6, b"out of device memory"), (-7, b"NCCL error"), (-99, b"unknown status")):
         assert lib.mmf_status_string(code) == text
 
 
