@@ -223,6 +223,223 @@ __global__ void __launch_bounds__(256) vault_stream_topk_kernel(const StreamPara
   }
 }
 
+// ---- TMA-staged form of the same kernel ------------------------------------------------------------------
+// The vault rows of a block are one contiguous byte range, so a producer thread streams them through a shared-memory
+// ring with 1-D bulk copies (cp.async.bulk + mbarrier complete_tx: UBLKCP in SASS), 64 KB = 32 fp32-exact rows per
+// stage, 3 stages: 128 KB in flight per SM while one stage is read -- against the 4 rows x 2 KB per warp that
+// registers allow above.  (First cut: 10 stages of 16 KB, one row per warp and stage -- 0.525 ms per query against
+// 0.367: every warp paid a barrier wait, a shuffle reduction and a hand-off per ROW, in lock-step with the others.)
+// tools/tma_stream_micro.cu: this loader alone streams whole rows at 7.3 TB/s (the register kernel: 5.5 TB/s).
+// 8 consumer warps take the rows of a stage (warp w: rows w*RPW .., 4 at a time), read their 16 elements per lane from shared
+// memory (conflict-free 128-bit reads) and do EXACTLY the arithmetic of the kernel above, in the same order, so the
+// two kernels return bit-identical scores; candidate buffers, thresholds, compaction and the last-block merge are
+// the same code.  Consumers never meet at a block barrier in the steady state: a named barrier every CHECK stages
+// lets them agree on a compaction (rare).
+constexpr int TMA_STAGE_BYTES = 65536, TMA_STAGES = 3, TMA_THREADS = 288;
+
+__device__ __forceinline__ u32 st_smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_init(u64* bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void st_mbar_expect_tx(u64* bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void st_mbar_arrive(u64* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void st_mbar_wait(u64* bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "SWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SDONE_%=;\n\t"
+      "bra SWAIT_%=;\n\t"
+      "SDONE_%=:\n\t}" ::"r"(st_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void st_bulk_load(void* dst, const void* src, u32 bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(st_smem_u32(dst)), "l"(src), "r"(bytes), "r"(st_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int QC, bool BF16, int KPL>
+__global__ void __launch_bounds__(TMA_THREADS, 1) vault_stream_tma_kernel(const StreamParams p) {
+  constexpr int ROW_BYTES = BF16 ? 1024 : 2048;
+  constexpr int SROWS = TMA_STAGE_BYTES / ROW_BYTES;     // rows per stage: 32 (fp32-exact) / 64 (bf16)
+  constexpr int RPW = SROWS / 8;                         // rows per consumer warp per stage: 4 / 8
+  constexpr int RCH = QC >= 8 ? 2 : 4;                   // ... processed 4 (2) at a time: 16 (8) independent 128-bit reads per lane
+  constexpr int CHECK = 1;                               // stages between compaction checks (<= 64 appends per query in between)
+  constexpr int C = 32 * KPL;
+  constexpr int LIMIT = C - 64;
+  constexpr int POOL = (QC * C > 2048) ? QC * C : 2048;
+  extern __shared__ __align__(128) unsigned char ring_raw[];
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ring_raw) + 127) & ~(uintptr_t)127);
+  __shared__ u64 pool[POOL];
+  u64 (*buf)[C] = reinterpret_cast<u64 (*)[C]>(pool);
+  __shared__ int cnt[QC];
+  __shared__ volatile float tau[QC];
+  __shared__ u32 tau_key[QC];
+  __shared__ int s_last;
+  __shared__ volatile int s_over[3];
+  __shared__ SelectSmem sel;
+  __shared__ __align__(8) u64 full_bar[TMA_STAGES], empty_bar[TMA_STAGES];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q0 = blockIdx.y * QC;
+  const int nq = min(QC, p.n_queries - q0);
+  const int k = p.top_k;
+  if (tid < QC) { cnt[tid] = 0; tau[tid] = -INFINITY; tau_key[tid] = 0; }
+  if (tid < 3) s_over[tid] = 0;
+  if (tid == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) { st_mbar_init(full_bar + s, 1); st_mbar_init(empty_bar + s, 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const long long row_begin = (long long)blockIdx.x * p.rows_per_cta;
+  const long long row_end = min(p.n_rows, row_begin + p.rows_per_cta);
+  const long long n_stages = row_end > row_begin ? (row_end - row_begin + SROWS - 1) / SROWS : 0;
+  const unsigned char* vault = reinterpret_cast<const unsigned char*>(p.vault);
+
+  if (warp == 8) {
+    // ===== producer =====
+    if (lane == 0) {
+      for (long long it = 0; it < n_stages; ++it) {
+        const int s = (int)(it % TMA_STAGES);
+        st_mbar_wait(empty_bar + s, (u32)(((it / TMA_STAGES) & 1) ^ 1));
+        const long long row = row_begin + it * SROWS;
+        const u32 bytes = (u32)(min((long long)SROWS, row_end - row) * ROW_BYTES);
+        st_mbar_expect_tx(full_bar + s, bytes);
+        st_bulk_load(ring + (size_t)s * TMA_STAGE_BYTES, vault + row * ROW_BYTES, bytes, full_bar + s);
+      }
+    }
+  } else {
+    // ===== consumers: lane owns elements 8*lane..+7 and 256+8*lane..+7 of every row (as the register kernel) =====
+    float q[QC][16];
+#pragma unroll
+    for (int qi = 0; qi < QC; ++qi) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        q[qi][e] = (qi < nq) ? p.qn[(long long)(q0 + qi) * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)] : 0.f;
+    }
+    for (long long it = 0; it < n_stages; ++it) {
+      const int s = (int)(it % TMA_STAGES);
+      u32 g_seen = 0;
+      if (it % CHECK == 0 && warp < nq && lane == 0) g_seen = *reinterpret_cast<volatile u32*>(p.g_tau + q0 + warp);
+      st_mbar_wait(full_bar + s, (u32)((it / TMA_STAGES) & 1));
+      const uint4* stage = reinterpret_cast<const uint4*>(ring + (size_t)s * TMA_STAGE_BYTES);
+#pragma unroll 1
+      for (int r0 = 0; r0 < RPW; r0 += RCH) {
+        float acc[RCH][QC];
+#pragma unroll
+        for (int r = 0; r < RCH; ++r) {
+          const uint4* rp = stage + (warp * RPW + r0 + r) * (ROW_BYTES / 16);
+          float v[16];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            float f[8];
+            unpack8(rp[c * 32 + lane], f, BF16);
+            if (!BF16) {
+              float g[8];
+              unpack8(rp[(c + 2) * 32 + lane], g, false);   // lo plane
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += g[e];   // exact: hi + lo fits 24 bits
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[c * 8 + e] = f[e];
+          }
+#pragma unroll
+          for (int qi = 0; qi < QC; ++qi) {
+            float a = 0.f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) a = fmaf(v[e], q[qi][e], a);
+            acc[r][qi] = a;
+          }
+        }
+        if (r0 + RCH == RPW) {                              // last rows of this warp read: the slot may be refilled
+          __syncwarp();
+          if (lane == 0) st_mbar_arrive(empty_bar + s);
+        }
+#pragma unroll
+        for (int r = 0; r < RCH; ++r)
+#pragma unroll
+          for (int qi = 0; qi < QC; ++qi) acc[r][qi] = warp_sum(acc[r][qi]);
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < RCH; ++r) {
+            const long long row = row_begin + it * SROWS + warp * RPW + r0 + r;
+            if (row < row_end) {
+#pragma unroll
+              for (int qi = 0; qi < QC; ++qi) {
+                if (qi < nq) {
+                  const float sc = BF16 ? acc[r][qi] : acc[r][qi] * MMF_SPLIT_INV_SCALE;
+                  if (!(sc < tau[qi])) {
+                    const int pos = atomicAdd(&cnt[qi], 1);
+                    buf[qi][pos] = pack_key(sc, p.row_base + (u32)row);
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if (it % CHECK == CHECK - 1 || it + 1 == n_stages) {
+        // adopt a better threshold found by another block; agree on a compaction (three rotating flags: the one
+        // written at check c is cleared after the barrier of check c+1, when nobody can still be reading it)
+        const int chk = (int)((it / CHECK) % 3);
+        if (warp < nq && lane == 0 && g_seen > tau_key[warp]) { tau_key[warp] = g_seen; tau[warp] = okey_inv(g_seen); }
+        if (tid < nq && cnt[tid] > LIMIT) s_over[chk] = 1;
+        consumer_barrier();
+        const int over = s_over[chk];
+        if (tid == 0) s_over[(chk + 2) % 3] = 0;
+        if (over) {
+          if (warp < nq && cnt[warp] > k) {
+            float t = 0.f;
+            const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
+            if (lane == 0) {
+              cnt[warp] = c;
+              const u32 tk = okey(t);
+              if (tk > tau_key[warp]) { tau_key[warp] = tk; tau[warp] = t; atomicMax(p.g_tau + q0 + warp, tk); }
+            }
+          }
+          consumer_barrier();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp < nq) {
+    float t;
+    const int c = warp_compact<KPL>(buf[warp], cnt[warp], k, &t);
+    u64* dst = p.part_keys + ((long long)blockIdx.x * p.n_queries + q0 + warp) * k;
+    for (int i = lane; i < c; i += 32) dst[i] = buf[warp][i];
+    if (lane == 0) p.part_cnt[(long long)blockIdx.x * p.n_queries + q0 + warp] = c;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const u32 ticket = atomicAdd(p.done + blockIdx.y, 1u);
+    s_last = (ticket == gridDim.x - 1);
+    if (s_last) p.done[blockIdx.y] = 0;     // self-reset for the next search
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int qi = 0; qi < nq; ++qi) {
+    const long long qg = q0 + qi;
+    CandidateLists src;
+    src.lists = p.part_keys + qg * k;
+    src.counts = p.part_cnt + qg;
+    src.n_lists = gridDim.x;
+    src.k_in = k;
+    src.list_stride = (long long)p.n_queries * k;
+    src.count_stride = p.n_queries;
+    block_select_topk(src, k, sel, pool, POOL, (u64)(*reinterpret_cast<volatile u32*>(p.g_tau + qg)) << 32, p.out_scores ? p.out_scores + qg * k : nullptr,
+                      p.out_rows ? p.out_rows + qg * k : nullptr, p.out_packed ? p.out_packed + qg * k : nullptr,
+                      p.out_disc ? p.out_disc + qg : nullptr, p.threshold);
+  }
+}
+
 // (n_lists, n_queries, k_in) packed candidates -> per-query sorted top-k.  One block per query.
 __global__ void __launch_bounds__(256) topk_merge_kernel(const u64* __restrict__ packed, int n_lists,
                                                          long long n_queries, int k_in, int top_k, double threshold,
@@ -265,6 +482,34 @@ static void launch_stream_k(int kpl, dim3 grid, cudaStream_t st, const StreamPar
   else vault_stream_topk_kernel<QC, BF16, 16><<<grid, 256, 0, st>>>(p);
 }
 
+template <int QC, bool BF16>
+static int launch_stream_tma_k(mmf_handle* h, int kpl, dim3 grid, cudaStream_t st, const StreamParams& p) {
+  const int smem = TMA_STAGES * TMA_STAGE_BYTES + 256;
+#define MMF_TMA_CASE(KPL_)                                                                                              \
+  do {                                                                                                                  \
+    auto kern = vault_stream_tma_kernel<QC, BF16, KPL_>;                                                                \
+    static unsigned long long attr_set = 0;                                                                             \
+    if (h->device >= 64 || !((attr_set >> h->device) & 1ull)) {                                                         \
+      MMF_CUDA_OK(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                    \
+      if (h->device < 64) attr_set |= 1ull << h->device;                                                                \
+    }                                                                                                                   \
+    kern<<<grid, TMA_THREADS, smem, st>>>(p);                                                                           \
+  } while (0)
+  if (kpl == 4) MMF_TMA_CASE(4);
+  else if (kpl == 8) MMF_TMA_CASE(8);
+  else MMF_TMA_CASE(16);
+#undef MMF_TMA_CASE
+  return MMF_OK;
+}
+
+template <bool BF16>
+static int launch_stream_tma_q(mmf_handle* h, int qc, int kpl, dim3 grid, cudaStream_t st, const StreamParams& p) {
+  if (qc == 1) return launch_stream_tma_k<1, BF16>(h, kpl, grid, st, p);
+  if (qc == 2) return launch_stream_tma_k<2, BF16>(h, kpl, grid, st, p);
+  if (qc == 4) return launch_stream_tma_k<4, BF16>(h, kpl, grid, st, p);
+  return launch_stream_tma_k<8, BF16>(h, kpl, grid, st, p);
+}
+
 template <bool BF16>
 static void launch_stream_q(int qc, int kpl, dim3 grid, cudaStream_t st, const StreamParams& p) {
   if (qc == 1) launch_stream_k<1, BF16>(kpl, grid, st, p);
@@ -283,7 +528,11 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   const int qc = Q <= 1 ? 1 : Q <= 2 ? 2 : Q <= 4 ? 4 : 8;
   const int gy = (Q + qc - 1) / qc;
   const int kpl = top_k <= 64 ? 4 : top_k <= 192 ? 8 : 16;
-  const long long target = (long long)h->sm_count * 4;
+  // TMA-staged kernel (option "stream_tma", default): one persistent block per SM and query chunk sweeps a contiguous
+  // slab of rows through a 160 KB shared-memory ring; the register kernel: 4 blocks per SM
+  // (8 queries per block with top_k > 192 would need 32 KB of candidate buffers next to the 192 KB ring: register kernel)
+  const bool tma = h->opt.stream_tma != 0 && !(qc == 8 && kpl == 16);
+  const long long target = (long long)h->sm_count * (tma ? 1 : 4);
   long long gx = std::max<long long>(1, (target + gy - 1) / gy);
   gx = std::min<long long>(gx, std::max<long long>(1, (h->vault_rows + 511) / 512));
   long long rows_per_cta = align_up((size_t)((h->vault_rows + gx - 1) / gx), 32);
@@ -322,8 +571,15 @@ int mmf_stream_search(mmf_handle* h, const float* queries, int64_t n_queries, in
   p.out_disc = out_disc;
   p.threshold = threshold;
   dim3 grid((unsigned)gx, (unsigned)gy);
-  if (h->vault_mode == MMF_VAULT_BF16) launch_stream_q<true>(qc, kpl, grid, st, p);
-  else launch_stream_q<false>(qc, kpl, grid, st, p);
+  if (tma) {
+    rc = h->vault_mode == MMF_VAULT_BF16 ? launch_stream_tma_q<true>(h, qc, kpl, grid, st, p)
+                                         : launch_stream_tma_q<false>(h, qc, kpl, grid, st, p);
+    if (rc != MMF_OK) return rc;
+  } else if (h->vault_mode == MMF_VAULT_BF16) {
+    launch_stream_q<true>(qc, kpl, grid, st, p);
+  } else {
+    launch_stream_q<false>(qc, kpl, grid, st, p);
+  }
   MMF_LAUNCH_OK(h);
   return MMF_OK;
 }

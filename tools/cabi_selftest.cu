@@ -233,7 +233,19 @@ int main(int argc, char** argv) {
     opt("epi_parity", -1);
     fails += !same(parity, stream, nq, k, "screened search, epi_parity=0 vs streaming kernel");
     opt("epi_parity", -1);
-    search(1, k, MMF_ALGO_STREAM, &ms_one, 50);
+    Result one = search(1, k, MMF_ALGO_STREAM, &ms_one, 50);
+    float ms_one_reg = 0, ms8 = 0, ms8_reg = 0;
+    Result eight = search(8, k, MMF_ALGO_STREAM, &ms8, 20);
+    opt("stream_tma", 0);
+    Result one_reg = search(1, k, MMF_ALGO_STREAM, &ms_one_reg, 50);
+    Result eight_reg = search(8, k, MMF_ALGO_STREAM, &ms8_reg, 20);
+    Result stream_reg = search(nq, k, MMF_ALGO_STREAM);
+    opt("stream_tma", 1);
+    fails += !same(one, one_reg, 1, k, "batch-1: TMA-staged vs register-staged streaming kernel");
+    fails += !same(eight, eight_reg, 8, k, "batch-8: TMA-staged vs register-staged streaming kernel");
+    fails += !same(stream, stream_reg, nq, k, "256 queries: TMA-staged vs register-staged streaming kernel");
+    printf("  streaming kernel: batch-1 TMA-staged %.4f ms (%.0f GB/s), register-staged %.4f ms (%.0f GB/s); batch-8 %.4f vs %.4f ms\n",
+           ms_one, rows_fp32 * 2048.0 / ms_one * 1e-6, ms_one_reg, rows_fp32 * 2048.0 / ms_one_reg * 1e-6, ms8, ms8_reg);
     printf("  search time: 3-pass %.3f ms (%.0f GB/s algorithmic), screened %.4f ms (%.0f GB/s algorithmic, %.0f GB/s of hi planes), "
            "screened with all warps on every tile %.4f ms, streaming x256 %.2f ms, batch-1 %.4f ms (%.0f GB/s)\n", ms_mma,
            rows_fp32 * 2048.0 / ms_mma * 1e-6, ms_screen, rows_fp32 * 2048.0 / ms_screen * 1e-6, rows_fp32 * 1024.0 / ms_screen * 1e-6,
@@ -287,6 +299,16 @@ int main(int argc, char** argv) {
     Result d = search(nq, 10, MMF_ALGO_MMA, &ms10p, 10);
     opt("epi_parity", -1);
     fails += !same(d, c, nq, 10, "top-10, epi_parity=1 vs default");
+    {
+      float t1 = 0, t0 = 0;
+      Result s1 = search(1, 10, MMF_ALGO_STREAM, &t1, 30);
+      opt("stream_tma", 0);
+      Result s0 = search(1, 10, MMF_ALGO_STREAM, &t0, 30);
+      opt("stream_tma", 1);
+      fails += !same(s1, s0, 1, 10, "bf16 batch-1: TMA-staged vs register-staged");
+      printf("  bf16 batch-1: TMA-staged %.4f ms (%.0f GB/s), register-staged %.4f ms (%.0f GB/s)\n", t1, rows_bf16 * 1024.0 / t1 * 1e-6, t0,
+             rows_bf16 * 1024.0 / t0 * 1e-6);
+    }
     const double fl = 2.0 * nq * rows_bf16 * 512;
     printf("  search time: top-100 %.3f ms (%.0f TFLOP/s), top-10 %.3f ms (%.0f TFLOP/s), top-10 + epi_parity %.3f ms (%.0f TFLOP/s)\n",
            ms100, fl / ms100 * 1e-9, ms10, fl / ms10 * 1e-9, ms10p, fl / ms10p * 1e-9);
@@ -312,6 +334,10 @@ int main(int argc, char** argv) {
         MM(mmf_vault_load(H, d_vault, 1, sh.n, 512, MMF_F32, mode == 0 ? MMF_VAULT_FP32 : MMF_VAULT_BF16, sh.off));
         snprintf(what, sizeof what, "%s N=%lld Q=%d k=%d off=%lld", mode ? "bf16" : "fp32", sh.n, sh.nq, sh.k, sh.off);
         Result stream = search(sh.nq, sh.k, MMF_ALGO_STREAM);
+        opt("stream_tma", 0);
+        Result stream_reg = search(sh.nq, sh.k, MMF_ALGO_STREAM);
+        opt("stream_tma", 1);
+        fails += !same(stream, stream_reg, sh.nq, sh.k, "   streaming kernel: TMA-staged vs register-staged");
         Result def = search(sh.nq, sh.k, MMF_ALGO_MMA);
         if (mode == 0 && sh.k <= 16) {
           fails += !same(def, stream, sh.nq, sh.k, what);                     // screened search: bit-identical
