@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the scoring hot path (BASELINE.json metric: vault queries/s + roofline).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--records auto|none|c1,c3,c4,kernels]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4] [--records auto|none|c1,c3,c4,kernels,c5]
                   [--impl reference]
 
 A step is one pass of the hot path over one batch of synthetic embeddings:
@@ -20,6 +20,8 @@ other BASELINE.json configs measured in the same run (each with its own timing, 
       csrc/shard.cu) + merge, with the local search, the all-gather and the merge timed separately and the result
       checked bit for bit against an unsharded search on rank 0                                        [every N]
   kernels  K1 cosine GB/s sweep up to 1M pairs, K5 fusion judge microseconds                            [N = 1]
+  c5  full batched analyze: random-init RoBERTa / EfficientNet / CLIP producers (stock PyTorch) feeding the scoring
+      kernels, data-parallel replicas; samples/s and the encoder / hot-path split of the step          [every N]
 
 `--impl reference` times the reference's own CPU algorithm (the oracle port of misinfo_forensics.py:438-464: per-query
 renormalisation of the whole vault in NumPy) on the host cores, rank 0 only.
@@ -676,6 +678,66 @@ def run_kernels(ctx, eng):
     return out
 
 
+def run_c5(ctx, batch=256, rows=1_000_000, top_k=5, steps=8, warmup=3, keep=None):
+    """C5 (BASELINE.json configs[4]): full batched analyze -- random-init PyTorch producers (RoBERTa-base heads,
+    EfficientNet-B0, CLIP ViT-B/32; bf16 autocast) feeding the scoring kernels through ONE library call, data-parallel
+    replicas (vault replicated per GPU, no collective).  Reports samples/s and how the step splits between the encoders
+    (stock PyTorch, out of scope) and this repo's kernels."""
+    import importlib.util
+    import mmf_b200
+    from mmf_b200 import synth
+    spec = importlib.util.spec_from_file_location("bench_c5", os.path.join(ROOT, "tools", "bench_c5.py"))
+    c5 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(c5)
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    prod = tuple(m.to(dev) for m in c5.build_producers())
+    if keep is not None and keep[1].n_total == rows and keep[1].mode == "fp32":
+        eng, vault = keep[0], keep[1]
+        own = False
+    else:
+        eng = mmf_b200.Engine(dev)
+        vault = mmf_b200.TruthVault(eng, gen_vault_rows(dev, rows, 0, rows), None, mode="fp32")
+        eng.fusion_load(synth.fusion_state_dict())
+        own = True
+    px, cid, rid = c5.synthetic_inputs(batch, dev, 100 + rank)
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            t, i, h = c5.encode(prod, px, cid, rid)
+        if ev:
+            ev[1].record()
+        out = eng.score_batch(t, i, h, None, top_k)
+        if ev:
+            ev[2].record()
+        return out
+    for _ in range(warmup):
+        step()
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for e in evs:
+        out = step(e)
+    verdict = out["verdict"].cpu()
+    ctx.barrier()
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    hot_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    step_ms = evs[0][0].elapsed_time(evs[-1][2]) / steps
+    clocks = sampler.stop() if sampler else None
+    step_ms, enc_ms, hot_ms = ctx.max_over_ranks([step_ms, enc_ms, hot_ms])
+    if own:
+        eng.close()
+    return {"metric": "analyze samples/s", "value": batch * world / (step_ms * 1e-3), "unit": "samples/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": step_ms, "scaling": "weak", "dtype": "bf16 autocast encoders + f32 hot path", "data": "synthetic",
+            "config": {"workload": "C5: batched analyze, random-init RoBERTa-base + EfficientNet-B0 + CLIP ViT-B/32 producers -> cosine + "
+                                   "vault top-%d + fusion judge" % top_k, "batch_per_gpu": batch, "vault_rows_per_gpu": rows,
+                       "parallelism": "replica x%d, vault replicated, no collective" % world},
+            "split": {"encoders_ms": enc_ms, "scoring_hot_path_ms": hot_ms, "hot_path_fraction": hot_ms / max(step_ms, 1e-9),
+                      "what": "CUDA events around the encoder forwards (stock PyTorch) and around mmf_score_batch (this repo), max over ranks"},
+            "fake_verdicts_rank0": int(verdict.sum()), "clocks": clocks}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -685,7 +747,7 @@ def main():
     ap.add_argument("--impl", default="mmf_b200", choices=["mmf_b200", "reference"])
     ap.add_argument("--algo", default="auto", choices=["auto", "stream", "mma"])
     ap.add_argument("--rows", type=int, default=0, help="override vault rows of every workload (debug only; the line then says so)")
-    ap.add_argument("--records", default="auto", help="auto (N = 1: c1,c3,c4,kernels; N > 1: c4) | none | comma list")
+    ap.add_argument("--records", default="auto", help="auto (N = 1: c1,c3,c4,kernels,c5; N > 1: c4,c5) | none | comma list")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wls = {k: dict(v) for k, v in WORKLOADS.items()}
@@ -701,7 +763,7 @@ def main():
     rank, world = ctx.rank, ctx.world
     records_arg = args.records.lower()
     if records_arg == "auto":
-        want = ["c1", "c3", "c4", "kernels"] if world == 1 else ["c4"]
+        want = ["c1", "c3", "c4", "kernels", "c5"] if world == 1 else ["c4", "c5"]
     elif records_arg == "none":
         want = []
     else:
@@ -733,6 +795,8 @@ def main():
         try:
             if name == "c4":
                 rec = run_c4(ctx, wls["c4"], min(args.steps, 10), 3, bool(args.rows))
+            elif name == "c5":
+                rec = run_c5(ctx, rows=wls["c2"]["rows"], keep=keep if args.workload == "c2" else None)
             elif name == "kernels":
                 if world > 1:
                     continue

@@ -222,6 +222,31 @@ class MisinfoForensics:
             p = torch.softmax(self.detector.forward_image(t), dim=1)[0, 1].item()
         return {"deepfake_score": p}
 
+    def analyze_text_batch(self, texts: Sequence[str], batch_size: int = 64) -> np.ndarray:
+        """analyze_text for many texts: (n,2) [ai_score, misinfo_score], the RoBERTa forward run on padded batches
+        (the producers are out of this repo's scope, but a per-sample loop around them would make the batched hot
+        path pointless).  batch_size=1 reproduces analyze_text's own forward exactly."""
+        out = np.zeros((len(texts), 2), np.float32)
+        for b0 in range(0, len(texts), max(1, batch_size)):
+            chunk = list(texts[b0:b0 + max(1, batch_size)])
+            inputs = self.roberta_tokenizer(chunk if len(chunk) > 1 else chunk[0], return_tensors="pt", max_length=512,
+                                            truncation=True, padding=True).to(self.device)
+            with torch.no_grad():
+                ai_logits, mis_logits = self.detector.forward_text(inputs["input_ids"], inputs["attention_mask"])
+                both = torch.stack([torch.softmax(ai_logits, dim=1)[:, 1], torch.softmax(mis_logits, dim=1)[:, 1]], dim=1)
+            out[b0:b0 + len(chunk)] = both.float().cpu().numpy()
+        return out
+
+    def analyze_image_batch(self, images: Sequence[Image.Image], batch_size: int = 64) -> np.ndarray:
+        """analyze_image for many (already opened) images: (n,) deepfake_score, EfficientNet on stacked batches."""
+        out = np.zeros(len(images), np.float32)
+        for b0 in range(0, len(images), max(1, batch_size)):
+            chunk = images[b0:b0 + max(1, batch_size)]
+            t = torch.stack([self.efficientnet_transform(im) for im in chunk]).to(self.device)
+            with torch.no_grad():
+                out[b0:b0 + len(chunk)] = torch.softmax(self.detector.forward_image(t), dim=1)[:, 1].float().cpu().numpy()
+        return out
+
     def _clip_image_embed(self, images: Sequence[Image.Image]) -> torch.Tensor:
         inputs = self.clip_processor(images=list(images) if len(images) > 1 else images[0], return_tensors="pt").to(self.device)
         with torch.no_grad():
@@ -456,11 +481,12 @@ class MisinfoForensics:
 
     # ------------------------------------------------------------------ batched analyze (new surface)
     def analyze_batch(self, texts: Sequence[Optional[str]], images: Sequence[Optional[Union[str, Image.Image]]],
-                      top_k: int = 5) -> List[Dict]:
-        """analyze() for a batch of (text, image) samples (either may be None, not both): producers run
-        per modality (one batched CLIP forward for all pairs), then ONE pass of the hot path
-        (cosine -> vault top-k -> fusion / fallback verdict) for the whole batch.  Per sample the result
-        equals analyze(text, image_path) -- same keys, same values."""
+                      top_k: int = 5, encoder_batch: int = 64) -> List[Dict]:
+        """analyze() for a batch of (text, image) samples (either may be None, not both): the producers run per
+        modality in batches of `encoder_batch` (RoBERTa heads, EfficientNet, one batched CLIP forward per tower), then
+        ONE pass of the hot path (cosine -> vault top-k -> fusion / fallback verdict) for the whole batch.  Per sample
+        the result equals analyze(text, image_path) -- same keys, same values, up to the encoders' own batched-vs-single
+        rounding (stock PyTorch, ~1e-6; encoder_batch=1 runs them exactly as analyze() does)."""
         n = len(texts)
         if len(images) != n:
             raise ValueError("texts and images must have the same length")
@@ -471,13 +497,16 @@ class MisinfoForensics:
             if not t and im is None:
                 raise ValueError("Provide at least one of: text, image_path, or video_path")
             if t:
-                ts = self.analyze_text(t)
-                head[i, 0], head[i, 1] = ts["ai_score"], ts["misinfo_score"]
                 mod[i] |= 1
             if im is not None:
                 pils[i] = self._to_pil_image(im)
-                head[i, 2] = self.analyze_image(pils[i])["deepfake_score"]
                 mod[i] |= 2
+        with_text = [i for i in range(n) if mod[i] & 1]
+        with_image = [i for i in range(n) if mod[i] & 2]
+        if with_text:
+            head[with_text, 0:2] = self.analyze_text_batch([texts[i] for i in with_text], encoder_batch)
+        if with_image:
+            head[with_image, 2] = self.analyze_image_batch([pils[i] for i in with_image], encoder_batch)
         t_emb = torch.zeros((n, 512), device=self.device)
         i_emb = torch.zeros((n, 512), device=self.device)
         vis = [i for i in range(n) if mod[i] & 2]

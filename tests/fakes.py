@@ -84,8 +84,9 @@ class FakeClipModel(nn.Module):
 
 class FakeTokenizer:
     def __call__(self, text, return_tensors="pt", max_length=512, truncation=True, padding=True):
-        return _Batch(input_ids=torch.tensor([[id_of_text(text)]], dtype=torch.long),
-                      attention_mask=torch.ones(1, 1, dtype=torch.long))
+        texts = [text] if isinstance(text, str) else list(text)
+        return _Batch(input_ids=torch.tensor([[id_of_text(t)] for t in texts], dtype=torch.long),
+                      attention_mask=torch.ones(len(texts), 1, dtype=torch.long))
 
 
 def _logit(p: float) -> float:

@@ -137,8 +137,9 @@ def test_bench_default_run_carries_the_records(monkeypatch, capsys):
     """what the driver runs (`bench.py --gpus 1 --steps K --warmup W`): the c2 headline plus the c1 / c3 / c4 / kernels records"""
     bench = _load_bench(monkeypatch)
     monkeypatch.setattr(bench, "run_kernels", lambda ctx, eng: {"cosine_pairs": [], "fusion_judge": []})   # 1M-pair sweeps: GPU-sized
+    monkeypatch.setattr(bench, "run_c5", lambda ctx, **kw: {"metric": "analyze samples/s", "value": 1.0})      # three encoders: GPU-sized
     d = _run(bench, monkeypatch, capsys, ["--rows", "2000", "--steps", "2", "--warmup", "3", "--no-cpu-baseline"])
-    assert d["cpu_baseline"] is None and set(d["records"]) == {"c1", "c3", "c4", "kernels"}
+    assert d["cpu_baseline"] is None and set(d["records"]) == {"c1", "c3", "c4", "kernels", "c5"}
     for name, rec in d["records"].items():
         assert "error" not in rec, (name, rec)
     assert d["records"]["c4"]["config"]["top_k"] == 100 and d["records"]["c4"]["roofline"]["bound"] == "tensor"

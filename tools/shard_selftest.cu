@@ -58,6 +58,7 @@ struct Shared {
   std::vector<int64_t> ref_rows;
   float ms[4][16];
   int fails[16];
+  int can[16];
   pthread_barrier_t bar;
 };
 static Shared S;
@@ -153,9 +154,19 @@ static void* rank_main(void* arg) {
   int can = 1;
   for (int r = 0; r < world && can; ++r)
     if (r != rank) { int ok = 0; CK(cudaDeviceCanAccessPeer(&ok, rank, r)); can = ok; }
+  for (int r = 0; r < world && can; ++r)
+    if (r != rank) {
+      const cudaError_t e = cudaDeviceEnablePeerAccess(r, 0);
+      cudaGetLastError();
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+        printf("  rank %d: cudaDeviceEnablePeerAccess(%d) failed: %s\n", rank, r, cudaGetErrorString(e));
+        can = 0;
+      }
+    }
+  S.can[rank] = can;
+  pthread_barrier_wait(&S.bar);
+  for (int r = 0; r < world; ++r) can = can && S.can[r];      // all ranks or none
   if (can) {
-    for (int r = 0; r < world; ++r)
-      if (r != rank) { cudaError_t e = cudaDeviceEnablePeerAccess(r, 0); if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(e); cudaGetLastError(); }
     void* buf = nullptr;
     CK(cudaMalloc(&buf, (size_t)S.xchg_bytes));
     CK(cudaMemset(buf, 0, (size_t)S.xchg_bytes));
