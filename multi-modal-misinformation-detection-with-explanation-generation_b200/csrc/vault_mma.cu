@@ -67,8 +67,16 @@
 #include <new>
 #include <vector>
 
+// Triage build (-DMMF_MMA_TRIAGE=1): the in-kernel cycle counters and the "debug" option bits are compiled in.  They are
+// OFF in the shipped library: the epilogue is latency-bound (one warp per scheduler retires an instruction every ~8 clk),
+// and the conditional clock reads + option tests were ~12 of its ~150 per-tile instructions.
+#ifndef MMF_MMA_TRIAGE
+#define MMF_MMA_TRIAGE 0
+#endif
+
 namespace mmf {
 
+constexpr bool TRIAGE = MMF_MMA_TRIAGE != 0;
 constexpr int TILE_M = 128;          // queries per tile   (UMMA M)
 constexpr int KBLK = 64;             // elements per k-block: 128 B rows, one 128B-swizzle atom
 constexpr int TILE_BYTES = 128 * KBLK * 2;   // 16 KB: [128 rows][64 elements]
@@ -529,7 +537,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         for (int kb = 0; kb < NUM_KBLK; kb += KBS, ++it) {
           const int s = it % STAGES;
           mbar_wait(empty_bar + s, ((it / STAGES) & 1) ^ 1);   // (compile-time STAGES: mul-shift, no division)
-          if (p.debug & 2) { if (leader) mbar_arrive(full_bar + s); continue; }
+          if (TRIAGE && (p.debug & 2)) { if (leader) mbar_arrive(full_bar + s); continue; }
           if (leader) mbar_expect_tx(full_bar + s, STAGE_BYTES * CG);
           const u32 fb = (CG == 2) ? mapa(smem_u32(full_bar + s), 0) : 0u;
 #pragma unroll
@@ -567,8 +575,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u32 q_addr = smem_u32(q_smem);
       const u32 st_addr = smem_u32(stage_smem);
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
-      const bool dbg = (p.debug & 8) != 0;
-      const long long t_begin = clock64();
+      const bool dbg = TRIAGE && (p.debug & 8) != 0;
+      const long long t_begin = dbg ? clock64() : 0;
       long long dbg_empty = 0, dbg_full = 0;
       int tp = sch.tp0, vt = sch.vt0;
       for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
@@ -581,7 +589,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
         const u32 acc = tile & 1;
         const long long t_e0 = dbg ? clock64() : 0;
-        if (!(p.debug & 4)) mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
+        if (!(TRIAGE && (p.debug & 4))) mbar_wait(tmem_empty + acc, ((tile >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         if (dbg) dbg_empty += clock64() - t_e0;
         const u32 d_tmem = tmem_base + acc * TILE_N;
@@ -589,7 +597,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         for (int kb0 = 0; kb0 < NUM_KBLK; kb0 += KBS, ++it) {
           const int s = it % STAGES;
           const long long t_f0 = dbg ? clock64() : 0;
-          if (!(p.debug & 4)) mbar_wait(full_bar + s, (it / STAGES) & 1);
+          if (!(TRIAGE && (p.debug & 4))) mbar_wait(full_bar + s, (it / STAGES) & 1);
           tcgen05_fence_after();
           if (dbg) dbg_full += clock64() - t_f0;
           if (elect_one()) {
@@ -628,7 +636,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           __syncwarp();
         }
       }
-      if ((p.debug & 8) && blockIdx.x == 0 && lane == 0 && tile > 0) {
+      if (dbg && blockIdx.x == 0 && lane == 0 && tile > 0) {
         mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
         const long long dt = clock64() - t_begin;
         printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block "
@@ -663,10 +671,13 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     bool valid_q = false;
     u32 tile = 0, g_prev = 0;
     int strip_u0 = 0;                                 // first tile of the current strip (warm-up: see the chunk loop)
-    const bool dbg = (p.debug & 8) != 0;
+    const bool dbg = TRIAGE && (p.debug & 8) != 0;
     long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
     int dbg_ncompact = 0;
     int tp = sch.tp0, vt = sch.vt0;
+    // (segment g of the L2-aware schedule holds one pair per query-tile group: every 8th segment takes the warm-up storm)
+    const bool storm_pair = pair < p.n_aligned ? (((pair / p.qtp) & 7) == 0) : (p.n_aligned == 0);
+    const int last_cols = (int)(p.n_rows - (long long)(p.v_tiles - 1) * TILE_N);   // valid columns of the LAST vault tile
     for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
       if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
       if (tp != cur_tp) {                             // new strip: flush the old one, reset state
@@ -733,10 +744,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       mbar_wait(tmem_full + acc, (tile >> 1) & 1);
       tcgen05_fence_after();
       const long long t_w1 = dbg ? clock64() : 0;
-      dbg_wait += t_w1 - t_w0;
-      // (segment g of the L2-aware schedule holds one pair per query-tile group: every 8th segment is designated)
-      const bool storm_pair = pair < p.n_aligned ? (((pair / p.qtp) & 7) == 0) : (p.n_aligned == 0);
-      if (KR > 0 && u == strip_u0 && !storm_pair && !(p.debug & 64)) {
+      if (dbg) dbg_wait += t_w1 - t_w0;
+      if (KR > 0 && u == strip_u0 && !storm_pair && !(TRIAGE && (p.debug & 64))) {
         // Warm-up of a strip.  With no bound yet, every element of the first chunk is a candidate event (a store
         // and an atomic, 32 distinct lines each per warp instruction), in every block at once: measured on the
         // screening pass, the first two tiles cost 55k of 347k clk, most of it contention on the 10 pool words per
@@ -756,12 +765,11 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
         __syncwarp();
       }
-      const long long row0 = (long long)vt * TILE_N;
-      const int n_cols = (int)min((long long)TILE_N, p.n_rows - row0);   // valid columns of this tile
-      const bool partial = n_cols < TILE_N;           // beyond n_cols the tile is TMA zero fill
-      const u32 row_id0 = p.row_base + (u32)row0;
+      const bool partial = vt == p.v_tiles - 1 && last_cols < TILE_N;     // beyond n_cols the tile is TMA zero fill
+      const int n_cols = partial ? last_cols : TILE_N;                    // valid columns of this tile
+      const u32 row_id0 = p.row_base + (u32)vt * (u32)TILE_N;
 #pragma unroll 1
-      for (int c = PARITY ? 0 : half; c < ((p.debug & 1) ? 0 : TILE_N / 32); c += PARITY ? 1 : 2) {
+      for (int c = PARITY ? 0 : half; c < ((TRIAGE && (p.debug & 1)) ? 0 : TILE_N / 32); c += PARITY ? 1 : 2) {
         u32 v[32];
         tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
         if (KR > 0 && u - strip_u0 < (PARITY ? 4 : 2) && (u != strip_u0 || c >= 2)) {
@@ -787,8 +795,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        if (p.debug & 16) { if (m8 == 12345.678f) cnt = 1; continue; }      // triage: tcgen05.ld + max tree only
-        if (!(m8 < MMF_TAU_F) && valid_q && !((p.debug & 32) && u - strip_u0 >= 2)) {   // triage bit 5: no events after the warm-up tiles
+        if (TRIAGE && (p.debug & 16)) { if (m8 == 12345.678f) cnt = 1; continue; }      // triage: tcgen05.ld + max tree only
+        if (!(m8 < MMF_TAU_F) && valid_q && !(TRIAGE && (p.debug & 32) && u - strip_u0 >= 2)) {   // triage bit 5: no events after the warm-up tiles
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (!(mx[i] < MMF_TAU_F)) {
@@ -817,7 +825,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         }
       }
       const long long t_f1 = dbg ? clock64() : 0;
-      dbg_filter += t_f1 - t_w1;
+      if (dbg) dbg_filter += t_f1 - t_w1;
       // hand the accumulator back FIRST: what follows overlaps the next MMAs
       tcgen05_fence_before();
       __syncwarp();
@@ -878,13 +886,13 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           if (t == t) atomicMax(g_tau, okey(t));
         }
         __syncwarp();
-        ++dbg_ncompact;
+        if (dbg) ++dbg_ncompact;
       }
       if (dbg) dbg_compact += clock64() - t_f1;
     }
 #undef MMF_TAU_F
     if (cur_tp >= 0) *cnt_out = cnt;
-    if ((p.debug & 8) && blockIdx.x == 0 && lane == 0)
+    if (dbg && blockIdx.x == 0 && lane == 0)
       printf("[mmf debug] epilogue warp %d: %u tiles; clk per OWN tile: wait %.0f, filter %.0f, arrive+compact %.0f; %d compactions, cnt %d\n",
              warp, tile, 2.0 * dbg_wait / tile, 2.0 * dbg_filter / tile, 2.0 * dbg_compact / tile, dbg_ncompact, cnt);
   }
