@@ -49,7 +49,7 @@ WORKLOADS = {
     "c4": dict(q=4096, rows=10_000_000, k=100, mode="bf16", desc="4096 queries vs 10M-row bf16 vault row-sharded over the ranks, top-100, all-gather merge"),
 }
 # committed `ncu --set full` summaries (profiles/<name>.ncu_summary.txt) of the dominant kernel of each workload
-NCU_SUMMARY = {"c2": "r02_c2_screen", "c3": "r01_final_c3", "c4": "r01_c4shard_hist", "c1": None}
+NCU_SUMMARY = {"c2": "r02_c2_screen", "c3": "r02_c3_stream_tma", "c4": "r02_c4shard_hist", "c1": None}
 
 
 def peaks():
@@ -314,27 +314,31 @@ def check_planted(rows0, scores0, batch, row_offset, tol, what):
 
 
 def hbm_roofline(ctx, wl_name, n_rows, Q, K, mode, search_ms, screened, rows_overridden):
+    """HBM roofline of the vault search.  `achieved` counts the bytes the search has to STREAM: N*D*elem (SURVEY.md 8d's
+    per-query figure) -- except for the screened fp32-exact search, which by construction reads only the fp16 hi planes
+    (N*D*2) plus a few dozen rows per query for the exact re-scoring; crediting it the full N*D*4 would report 1.2x the
+    measured HBM peak for bytes that never move, so that figure is kept aside as `frac_vs_survey_bytes`."""
     elem = 2 if mode == "bf16" else 4
-    nbytes = float(n_rows) * 512 * elem
+    survey_bytes = float(n_rows) * 512 * elem
+    nbytes = float(n_rows) * 512 * 2 if screened else survey_bytes
     achieved = nbytes / (search_ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": ctx.hbm_peak, "unit": "GB/s", "frac": achieved / ctx.hbm_peak,
             "traffic": None, "kernel": "vault search (query prep + search + top-k select)",
-            "algorithmic_bytes_per_launch": nbytes,
+            "algorithmic_bytes_per_launch": nbytes, "survey_bytes_per_launch": survey_bytes,
+            "frac_vs_survey_bytes": survey_bytes / (search_ms * 1e-3) / 1e9 / ctx.hbm_peak,
             "tensor_tflops_algorithmic": 2.0 * Q * n_rows * 512 / (search_ms * 1e-3) / 1e12}
     if Q >= 16:
         # fp32-exact tcgen05 path.  top_k <= 16 (default): SCREENED search -- one f16 pass over the hi planes (half of the
         # stored bytes, a third of the MMA work), then exact fp32 re-scoring of the rows inside the proven error band
-        # (DESIGN.md 9).  Otherwise: 3 f16 passes.  Only 2*Q*N*D flop and N*D*4 bytes are credited either way.
+        # (DESIGN.md 9).  Otherwise: 3 f16 passes.  Only 2*Q*N*D flop are credited either way.
         passes = 3 if (mode == "fp32" and not screened) else 1
         issued = passes * roof["tensor_tflops_algorithmic"]
-        streamed = float(n_rows) * 512 * (2 if (screened or mode == "bf16") else 4)
         roof.update({"mma_passes": passes, "tensor_tflops_issued": issued, "tensor_frac_issued": issued / ctx.tf_peak,
                      "variant": "screened (hi-plane pass + exact re-scoring)" if screened else "%d-pass" % passes,
-                     "bytes_streamed_per_launch": streamed,
-                     "hbm_frac_streamed": streamed / (search_ms * 1e-3) / 1e9 / ctx.hbm_peak,
-                     "note": ("the screened search streams only the fp16 hi planes (N*D*2 bytes) and re-scores the few rows inside "
-                              "the error band from hi+lo; `achieved`/`frac` credit the algorithmic N*D*4 bytes of SURVEY.md 8(d), "
-                              "`hbm_frac_streamed` is what DRAM actually delivers") if screened else
+                     "bytes_streamed_per_launch": nbytes, "hbm_frac_streamed": roof["frac"],
+                     "note": ("the screened search streams only the fp16 hi planes (N*D*2 bytes, what `achieved` counts) and re-scores "
+                              "the few rows inside the error band from hi+lo; at 256 queries it is balanced between HBM and the tensor "
+                              "pipe (256 flop/B vs a ridge of ~250), so neither roof is reachable alone") if screened else
                              "tensor-bound once the MMA passes are counted; the HBM fraction is the algorithmic roofline"})
     summary = NCU_SUMMARY.get(wl_name)
     traffic = ncu_traffic(summary) if ctx.world == 1 and not rows_overridden else None

@@ -54,10 +54,22 @@ def queries(n_q: int, n_vault: int, dim: int = D, seed: int = QUERY_SEED, plant_
     n_plant = int(round(n_q * plant_frac)) if n_vault > 0 else 0
     if n_plant:
         which = g.choice(n_q, n_plant, replace=False)
+        blocks = {}                         # 64Ki-row blocks of the seeded vault already generated in this call: a planted
+                                            # row costs one block (33M normals), not one block per planted query
+
+        def vault_row(row: int, block: int = 65536) -> np.ndarray:
+            b = row // block
+            if b not in blocks:
+                if len(blocks) >= 6:
+                    blocks.pop(next(iter(blocks)))
+                blocks[b] = np.random.default_rng([vault_seed, b]).standard_normal((block, dim), dtype=np.float32)
+            out = blocks[b][row - b * block:row - b * block + 1].copy()
+            out /= np.linalg.norm(out, axis=1, keepdims=True)       # the very operations of vault_rows(1, row, dim, vault_seed)
+            return out[0]
         for j, qi in enumerate(which):
             row = int(g.integers(0, n_vault))
             c = PLANT_COSINES[j % len(PLANT_COSINES)]
-            q[qi] = planted_query(vault_rows(1, row, dim, vault_seed)[0], c, g)
+            q[qi] = planted_query(vault_row(row), c, g)
             rows[qi], cosv[qi] = row, c
     if scale:   # embeddings reach the hot path un-normalised; exercise the normalise step
         q *= g.uniform(0.5, 20.0, size=(n_q, 1)).astype(np.float32)
