@@ -675,8 +675,6 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     long long dbg_wait = 0, dbg_filter = 0, dbg_compact = 0;
     int dbg_ncompact = 0;
     int tp = sch.tp0, vt = sch.vt0;
-    // (segment g of the L2-aware schedule holds one pair per query-tile group: every 8th segment takes the warm-up storm)
-    const bool storm_pair = pair < p.n_aligned ? (((pair / p.qtp) & 7) == 0) : (p.n_aligned == 0);
     const int last_cols = (int)(p.n_rows - (long long)(p.v_tiles - 1) * TILE_N);   // valid columns of the LAST vault tile
     for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
       if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
@@ -745,33 +743,60 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       tcgen05_fence_after();
       const long long t_w1 = dbg ? clock64() : 0;
       if (dbg) dbg_wait += t_w1 - t_w0;
-      if (KR > 0 && u == strip_u0 && !storm_pair && !(TRIAGE && (p.debug & 64))) {
-        // Warm-up of a strip.  With no bound yet, every element of the first chunk is a candidate event (a store
-        // and an atomic, 32 distinct lines each per warp instruction), in every block at once: measured on the
-        // screening pass, the first two tiles cost 55k of 347k clk, most of it contention on the 10 pool words per
-        // query.  One storm per QUERY is enough to seed the pool, so only every 8th pair takes it; the others wait
-        // here (bounded) until all of their query's buckets are filled, and start with the grid-wide bound.
-        const long long t_end = clock64() + 30000;
-        for (;;) {
+      const bool partial = vt == p.v_tiles - 1 && last_cols < TILE_N;     // beyond n_cols the tile is TMA zero fill
+      const int n_cols = partial ? last_cols : TILE_N;                    // valid columns of this tile
+      const u32 row_id0 = p.row_base + (u32)vt * (u32)TILE_N;
+      if (KR > 0 && u - strip_u0 < 2 && __any_sync(0xFFFFFFFFu, tau_acc == -INFINITY && valid_q)) {    // (warp-uniform)
+        // Warm-up of a strip: no bound yet.  Filtering without one makes every element a candidate event (a store and
+        // an atomic, 32 distinct lines each per warp instruction) in every block at once -- measured on the screening
+        // pass, 50k of 324k clk.  Instead the grid SEEDS the bucket pool first: each thread publishes the maximum of
+        // each of its chunks of this tile (one atomic per 32 rows; the chunks of all blocks are distinct rows, and a
+        // row always goes to its own bucket), waits (bounded) until every bucket of its query has a value -- all
+        // blocks seed at the same time, ~300 chunk maxima per query -- and only then filters the tile, which is still
+        // in tensor memory, against a bound that is already the ~25th best of the first ~10k rows.
+        auto pool_min = [&]() {
           u32 mn = 0xFFFFFFFFu;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint4 x = __ldcv(reinterpret_cast<const uint4*>(pool) + i);
             mn = min(min(mn, x.x), min(min(x.y, x.z), x.w));
           }
-          if (mn != 0u) { tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale); break; }
-          if (!valid_q || clock64() > t_end) break;
-          __nanosleep(400);
-        }
-        __syncwarp();
-      }
-      const bool partial = vt == p.v_tiles - 1 && last_cols < TILE_N;     // beyond n_cols the tile is TMA zero fill
-      const int n_cols = partial ? last_cols : TILE_N;                    // valid columns of this tile
-      const u32 row_id0 = p.row_base + (u32)vt * (u32)TILE_N;
+          return mn;
+        };
+        u32 mn = pool_min();
+        if (__any_sync(0xFFFFFFFFu, mn == 0u && valid_q) && !(TRIAGE && (p.debug & 64))) {
 #pragma unroll 1
-      for (int c = PARITY ? 0 : half; c < ((TRIAGE && (p.debug & 1)) ? 0 : TILE_N / 32); c += PARITY ? 1 : 2) {
-        u32 v[32];
-        tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
+          for (int c = PARITY ? 0 : half; c < TILE_N / 32; c += PARITY ? 1 : 2) {
+            u32 v[32];
+            tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
+            tmem_wait_ld();
+            float best = -INFINITY;
+            int bj = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = (partial && c * 32 + j >= n_cols) ? -INFINITY : __uint_as_float(v[j]);
+              if (a > best) { best = a; bj = j; }
+            }
+            if (valid_q && best > -INFINITY) {
+              const u32 ub = __float_as_uint((SPLIT || SCREEN) ? best * p.inv_scale : best);
+              const u32 row = row_id0 + c * 32 + bj;
+              atomicMax(pool + pool_bucket(row, (u32)k), ub ^ ((u32)((int)ub >> 31) | 0x80000000u));
+            }
+          }
+          const long long t_end = clock64() + 20000;
+          for (;;) {
+            mn = pool_min();
+            if (mn != 0u || !valid_q || clock64() > t_end) break;
+            __nanosleep(200);
+          }
+          __syncwarp();
+        }
+        if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
+      }
+      // The chunks of a tile are software-pipelined over two register buffers: the tcgen05.ld of the next chunk is in
+      // flight while the current one is filtered (tcgen05.wait::ld waits for every outstanding load of the thread, so
+      // the next load is issued right after the wait for the current one).
+      auto refresh_bound = [&](int c) {
         if (KR > 0 && u - strip_u0 < (PARITY ? 4 : 2) && (u != strip_u0 || c >= 2)) {
           // warm-up of a strip: a list's own threshold is still loose (the 10th best of a few dozen rows) while the
           // whole grid has already seen thousands, so re-read the bucket pool before EVERY chunk of the first two
@@ -785,7 +810,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           }
           if (mn != 0u && mn != 0xFFFFFFFFu) tau_acc = fmaxf(tau_acc, okey_inv(mn) * acc_scale);
         }
-        tmem_wait_ld();
+      };
+      auto filter_chunk = [&](int c, const u32 (&v)[32]) {
         // fast path (almost always): chunk maximum below the threshold.  A max tree keeps the
         // dependent chain short.  (fmaxf drops a NaN next to a number; vaults with NaN rows never
         // reach this kernel, see mmf_mma_supported.)
@@ -795,7 +821,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           mx[i] = fmaxf(fmaxf(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])),
                         fmaxf(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
-        if (TRIAGE && (p.debug & 16)) { if (m8 == 12345.678f) cnt = 1; continue; }      // triage: tcgen05.ld + max tree only
+        if (TRIAGE && (p.debug & 16)) { if (m8 == 12345.678f) cnt = 1; return; }      // triage: tcgen05.ld + max tree only
         if (!(m8 < MMF_TAU_F) && valid_q && !(TRIAGE && (p.debug & 32) && u - strip_u0 >= 2)) {   // triage bit 5: no events after the warm-up tiles
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -823,13 +849,38 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
             }
           }
         }
+            };
+      auto release_acc = [&]() {
+        // hand the accumulator back as soon as its last column is in registers: the filtering of what has been read
+        // overlaps the next MMAs into this buffer
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
+      };
+      if (TRIAGE && (p.debug & 1)) {
+        release_acc();
+      } else {
+        constexpr int C_STEP = PARITY ? 1 : 2, N_CHUNKS = TILE_N / 32;
+        const int c_first = PARITY ? 0 : half;
+        const u32 t_acc = lane_base + acc * TILE_N;
+        u32 va[32], vb[32];
+        tmem_ld32(t_acc + c_first * 32, va);
+        tmem_ld32(t_acc + (c_first + C_STEP) * 32, vb);
+#pragma unroll 1
+        for (int c = c_first; c < N_CHUNKS; c += 2 * C_STEP) {
+          const bool last = c + 2 * C_STEP >= N_CHUNKS;
+          refresh_bound(c);
+          tmem_wait_ld();
+          if (last) release_acc();
+          filter_chunk(c, va);
+          if (!last) tmem_ld32(t_acc + (c + 2 * C_STEP) * 32, va);
+          refresh_bound(c + C_STEP);
+          filter_chunk(c + C_STEP, vb);
+          if (!last) tmem_ld32(t_acc + (c + 3 * C_STEP) * 32, vb);
+        }
       }
       const long long t_f1 = dbg ? clock64() : 0;
       if (dbg) dbg_filter += t_f1 - t_w1;
-      // hand the accumulator back FIRST: what follows overlaps the next MMAs
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tmem_empty_l + acc * 8); else mbar_arrive(tmem_empty + acc); }
       if (KR == 0 && valid_q && (tile < 96 ? (tile & 3) == 3 : (tile & 31) == 31)) {
         // large top_k: refresh the grid-wide bound from the bucket pool -- every 4th tile while the
         // thresholds still move fast (half of all candidate events happen in the first few thousand rows),

@@ -193,14 +193,17 @@ int main(int argc, char** argv) {
     MM(mmf_vault_load(H, d_vault, 1, 1000000, 512, MMF_F32, MMF_VAULT_FP32, 0));
     struct Arm { const char* name; int parity, debug; };
     const Arm arms[] = {{"all warps on every tile", 0, 0}, {"parity (warp sets alternate tiles)", 1, 0},
-                        {"all warps, no warm-up wait", 0, 64}, {"parity, no warm-up wait", 1, 64}};
+                        {"library default (by strip length)", -1, 0}};
     const int n_arms = sizeof arms / sizeof arms[0], rounds = 7;
     std::vector<std::vector<float>> t(n_arms);
+    Result first;
     for (int r = 0; r < rounds; ++r)
       for (int a = 0; a < n_arms; ++a) {
         opt("epi_parity", arms[a].parity); opt("debug", arms[a].debug);
         float ms = 0;
-        search(256, 10, MMF_ALGO_MMA, &ms, 40);
+        Result res = search(256, 10, MMF_ALGO_MMA, &ms, 40);
+        if (r == 0 && a == 0) first = res;
+        else if (r == 0) fails += !same(res, first, 256, 10, arms[a].name);
         t[a].push_back(ms);
       }
     for (int a = 0; a < n_arms; ++a) {
@@ -208,6 +211,27 @@ int main(int argc, char** argv) {
       for (size_t i = 0; i < v.size(); ++i) for (size_t j = i + 1; j < v.size(); ++j) if (v[j] < v[i]) { float x = v[i]; v[i] = v[j]; v[j] = x; }
       printf("  %-36s min %.4f  median %.4f  max %.4f ms\n", arms[a].name, v[0], v[v.size() / 2], v.back());
     }
+    // the long-strip shape (bf16 vault, 4096 queries, top-10)
+    fill_rows<<<(unsigned)((1250000ll * 512 + 255) / 256), 256>>>(d_vault, 1250000, 21);
+    fill_rows<<<(4096 * 512 + 255) / 256, 256>>>(d_q, 4096, 12);
+    CK(cudaDeviceSynchronize());
+    MM(mmf_vault_load(H, d_vault, 1, 1250000, 512, MMF_F32, MMF_VAULT_BF16, 0));
+    for (int a = 0; a < n_arms; ++a) t[a].clear();
+    for (int r = 0; r < 3; ++r)
+      for (int a = 0; a < n_arms; ++a) {
+        opt("epi_parity", arms[a].parity);
+        float ms = 0;
+        Result res = search(4096, 10, MMF_ALGO_MMA, &ms, 5);
+        if (r == 0 && a == 0) first = res;
+        else if (r == 0) fails += !same(res, first, 4096, 10, arms[a].name);
+        t[a].push_back(ms);
+      }
+    for (int a = 0; a < n_arms; ++a) {
+      std::vector<float> v = t[a];
+      for (size_t i = 0; i < v.size(); ++i) for (size_t j = i + 1; j < v.size(); ++j) if (v[j] < v[i]) { float x = v[i]; v[i] = v[j]; v[j] = x; }
+      printf("  bf16 4096 x 1.25M top-10: %-36s min %.4f  median %.4f ms\n", arms[a].name, v[0], v[v.size() / 2]);
+    }
+    printf("tune: %d mismatches\n", fails);
     mmf_destroy(H);
     return 0;
   }
