@@ -750,10 +750,10 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         // Warm-up of a strip: no bound yet.  Filtering without one makes every element a candidate event (a store and
         // an atomic, 32 distinct lines each per warp instruction) in every block at once -- measured on the screening
         // pass, 50k of 324k clk.  Instead the grid SEEDS the bucket pool first: each thread publishes the maximum of
-        // each of its chunks of this tile (one atomic per 32 rows; the chunks of all blocks are distinct rows, and a
-        // row always goes to its own bucket), waits (bounded) until every bucket of its query has a value -- all
-        // blocks seed at the same time, ~300 chunk maxima per query -- and only then filters the tile, which is still
-        // in tensor memory, against a bound that is already the ~25th best of the first ~10k rows.
+        // its part of this tile (one atomic; the tiles of all blocks are distinct rows, and a row always goes to its
+        // own bucket), waits (bounded) until every bucket of its query has a value -- all blocks seed at the same
+        // time, one maximum per 64 or 128 rows -- and only then filters the tile, which is still in tensor memory,
+        // against a bound that is already the ~25th best of the first ~10k rows.
         auto pool_min = [&]() {
           u32 mn = 0xFFFFFFFFu;
 #pragma unroll
@@ -765,23 +765,23 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         };
         u32 mn = pool_min();
         if (__any_sync(0xFFFFFFFFu, mn == 0u && valid_q) && !(TRIAGE && (p.debug & 64))) {
+          float best = -INFINITY;
+          int bj = 0;
 #pragma unroll 1
           for (int c = PARITY ? 0 : half; c < TILE_N / 32; c += PARITY ? 1 : 2) {
             u32 v[32];
             tmem_ld32(lane_base + acc * TILE_N + c * 32, v);
             tmem_wait_ld();
-            float best = -INFINITY;
-            int bj = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float a = (partial && c * 32 + j >= n_cols) ? -INFINITY : __uint_as_float(v[j]);
-              if (a > best) { best = a; bj = j; }
+              if (a > best) { best = a; bj = c * 32 + j; }
             }
-            if (valid_q && best > -INFINITY) {
-              const u32 ub = __float_as_uint((SPLIT || SCREEN) ? best * p.inv_scale : best);
-              const u32 row = row_id0 + c * 32 + bj;
-              atomicMax(pool + pool_bucket(row, (u32)k), ub ^ ((u32)((int)ub >> 31) | 0x80000000u));
-            }
+          }
+          if (valid_q && best > -INFINITY) {       // ONE atomic per thread: 10 words per query take the seeds of the whole grid
+            const u32 ub = __float_as_uint((SPLIT || SCREEN) ? best * p.inv_scale : best);
+            const u32 row = row_id0 + bj;
+            atomicMax(pool + pool_bucket(row, (u32)k), ub ^ ((u32)((int)ub >> 31) | 0x80000000u));
           }
           const long long t_end = clock64() + 20000;
           for (;;) {
@@ -1128,9 +1128,15 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   __shared__ u64 staging[STAGING];
   __shared__ int slots[MERGE_MAX_SLOTS];
   __shared__ int n_slots;
+  __shared__ u32 warp_cnt[8];
   const int qg = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (p.g_tau[qg] == 0xFFFFFFFFu) { nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc); return; }
+  // this lane's 16 elements of the normalised query: 8*lane..+7 and 256+8*lane..+7 (as vault_stream.cu); loaded first,
+  // the latency hides behind the staging of the candidates
+  float q[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) q[e] = p.qn[(long long)qg * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)];
   // bounds on the k-th best APPROXIMATE score; candidates down to margin below it may matter
   const u32 g = published_bound(p, qg);
   const u64 min_key = g ? (u64)okey(okey_inv(g) - p.margin) << 32 : 0ull;
@@ -1140,54 +1146,81 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
     if (tid == 0) *p.ovf = 1;
     return;
   }
-  const bool by_rank = n_staged <= (u32)RANK_SELECT_MAX;
   select_staged(src, n_staged, staging, STAGING, min_key, p.top_k, sel);      // approximate top-k of the staged candidates
   const u64 kth = sel.win[p.top_k - 1];                          // 0: fewer than top_k candidates -> keep all
   const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - p.margin) << 32 : 0ull;
   __syncthreads();
 
-  // this lane's 16 elements of the normalised query: 8*lane..+7 and 256+8*lane..+7 (as vault_stream.cu)
-  float q[16];
+  // Compact the candidates inside the band to the front of the staging array (in place, 256 at a time: a round's
+  // reads are done before its writes, which land below the round's end), so that the 8 warps share the rows to
+  // re-score evenly -- each row is a 2 KB read from HBM, latency-bound.
+  u32 n_band = 0;
+  for (u32 base = 0; base < n_staged; base += 256) {
+    const u32 i = base + tid;
+    const u64 key = i < n_staged ? staging[i] : 0ull;
+    const bool in = key != 0ull && key >= cut;
+    const u32 bal = __ballot_sync(FULL, in);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    u32 off = n_band, tot = 0;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) q[e] = p.qn[(long long)qg * MMF_DIM + (e >> 3) * 256 + lane * 8 + (e & 7)];
-  for (u32 i = warp; i < n_staged; i += 8) {
-    const u64 key = staging[i];
-    u64 exact = 0ull;                                            // dropped unless inside the band
-    if (key >= cut) {                                            // warp-uniform
-      const u32 row = (u32)key;
-      const uint4* rp = vault + (long long)(row - p.row_base) * 128;   // [hi 64 x uint4 | lo 64 x uint4]
-      uint4 ld[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) ld[c] = __ldg(rp + c * 32 + lane);
-      float v[16];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const u32 hx[4] = {ld[c].x, ld[c].y, ld[c].z, ld[c].w};
-        const u32 lx[4] = {ld[c + 2].x, ld[c + 2].y, ld[c + 2].z, ld[c + 2].w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hx[j]));
-          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lx[j]));
-          v[c * 8 + 2 * j] = hf.x + lf.x;                        // exact: hi + lo fits 24 bits
-          v[c * 8 + 2 * j + 1] = hf.y + lf.y;
-        }
-      }
-      float a = 0.f;
-#pragma unroll
-      for (int e = 0; e < 16; ++e) a = fmaf(v[e], q[e], a);
-      a = warp_sum(a);
-      exact = pack_key(a * MMF_SPLIT_INV_SCALE, row);
+    for (int w = 0; w < 8; ++w) {
+      const u32 c = warp_cnt[w];
+      if (w < warp) off += c;
+      tot += c;
     }
+    if (in) staging[off + __popc(bal & ((1u << lane) - 1u))] = key;
+    n_band += tot;
+    __syncthreads();
+  }
+
+  // exact score of a vault row against this query: same element order and reduction tree as vault_stream.cu
+  auto load_row = [&](u32 row, uint4 (&ld)[4]) {
+    const uint4* rp = vault + (long long)(row - p.row_base) * 128;   // [hi 64 x uint4 | lo 64 x uint4]
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ld[c] = __ldg(rp + c * 32 + lane);
+  };
+  auto exact_key = [&](u32 row, const uint4 (&ld)[4]) {
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const u32 hx[4] = {ld[c].x, ld[c].y, ld[c].z, ld[c].w};
+      const u32 lx[4] = {ld[c + 2].x, ld[c + 2].y, ld[c + 2].z, ld[c + 2].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hx[j]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lx[j]));
+        v[c * 8 + 2 * j] = hf.x + lf.x;                        // exact: hi + lo fits 24 bits
+        v[c * 8 + 2 * j + 1] = hf.y + lf.y;
+      }
+    }
+    float a = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) a = fmaf(v[e], q[e], a);
+    a = warp_sum(a);
+    return pack_key(a * MMF_SPLIT_INV_SCALE, row);
+  };
+  for (u32 i = warp; i < n_band; i += 16) {                      // two rows in flight per warp
+    const bool two = i + 8 < n_band;                             // (warp-uniform)
+    const u32 row0 = (u32)staging[i], row1 = two ? (u32)staging[i + 8] : row0;
+    uint4 ld0[4], ld1[4];
+    load_row(row0, ld0);
+    if (two) load_row(row1, ld1);
+    const u64 e0 = exact_key(row0, ld0);
+    const u64 e1 = two ? exact_key(row1, ld1) : 0ull;
     __syncwarp();
-    if (lane == 0) staging[i] = exact;
+    if (lane == 0) {
+      staging[i] = e0;
+      if (two) staging[i + 8] = e1;
+    }
   }
   __syncthreads();
   // select + sort the exact keys: one list in shared memory, read in place
-  if (by_rank) {
-    block_rank_select(staging, (int)n_staged, p.top_k, sel);
+  if (n_band <= (u32)RANK_SELECT_MAX) {
+    block_rank_select(staging, (int)n_band, p.top_k, sel);
   } else {
     CandidateLists ex;
-    ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n_staged; ex.list_stride = 0; ex.count_stride = 0;
+    ex.lists = staging; ex.counts = nullptr; ex.n_lists = 1; ex.k_in = (int)n_band; ex.list_stride = 0; ex.count_stride = 0;
     block_select_topk(ex, p.top_k, sel, staging, 0, 0ull, nullptr, nullptr, nullptr, nullptr, 0.0);
   }
   write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
