@@ -334,11 +334,15 @@ def hbm_roofline(ctx, wl_name, n_rows, Q, K, mode, search_ms, screened, rows_ove
         passes = 3 if (mode == "fp32" and not screened) else 1
         issued = passes * roof["tensor_tflops_algorithmic"]
         roof.update({"mma_passes": passes, "tensor_tflops_issued": issued, "tensor_frac_issued": issued / ctx.tf_peak,
+                     "tensor_frac_sustained": issued / ctx.tf_sustained,
                      "variant": "screened (hi-plane pass + exact re-scoring)" if screened else "%d-pass" % passes,
                      "bytes_streamed_per_launch": nbytes, "hbm_frac_streamed": roof["frac"],
                      "note": ("the screened search streams only the fp16 hi planes (N*D*2 bytes, what `achieved` counts) and re-scores "
-                              "the few rows inside the error band from hi+lo; at 256 queries it is balanced between HBM and the tensor "
-                              "pipe (256 flop/B vs a ridge of ~250), so neither roof is reachable alone") if screened else
+                              "the few rows inside the error band from hi+lo; at 256 queries it sits ON the ridge (256 flop/B against "
+                              "bf16 peak / HBM peak ~ 250): the MMAs of one pass over the hi planes take longer at the measured tensor "
+                              "peak than the bytes take at the measured HBM peak, and under tensor load the SM clock is ~1.4-1.5 GHz "
+                              "(clock64 / globaltimer inside the kernel, profiles/r02_screen_triage_clock.log), so `tensor_frac_issued` / "
+                              "`tensor_frac_sustained` bound this search as tightly as `frac` does") if screened else
                              "tensor-bound once the MMA passes are counted; the HBM fraction is the algorithmic roofline"})
     summary = NCU_SUMMARY.get(wl_name)
     traffic = ncu_traffic(summary) if ctx.world == 1 and not rows_overridden else None

@@ -577,6 +577,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       const u64 desc_hi = (u64)((1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61));
       const bool dbg = TRIAGE && (p.debug & 8) != 0;
       const long long t_begin = dbg ? clock64() : 0;
+      unsigned long long ns_begin = 0;
+      if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_begin));
       long long dbg_empty = 0, dbg_full = 0;
       int tp = sch.tp0, vt = sch.vt0;
       for (int u = 0; u < sch.n_tiles; ++u, ++tile, ++vt) {
@@ -639,9 +641,12 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       if (dbg && blockIdx.x == 0 && lane == 0 && tile > 0) {
         mbar_wait(tmem_full + ((tile - 1) & 1), ((tile - 1) >> 1) & 1);     // last accumulator complete
         const long long dt = clock64() - t_begin;
+        unsigned long long ns_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns_end));
         printf("[mmf debug] block 0: %u tiles, %u k-blocks, %lld clk in the MMA loop -> %.1f clk per k-block "
-               "(waiting: accumulator free %.1f, operands landed %.1f)\n", tile, it * KBS, dt,
-               (double)dt / (it * KBS), (double)dbg_empty / (it * KBS), (double)dbg_full / (it * KBS));
+               "(waiting: accumulator free %.1f, operands landed %.1f); %.1f us -> SM clock %.0f MHz\n", tile, it * KBS, dt,
+               (double)dt / (it * KBS), (double)dbg_empty / (it * KBS), (double)dbg_full / (it * KBS),
+               (double)(ns_end - ns_begin) * 1e-3, (double)dt / ((double)(ns_end - ns_begin) * 1e-3));
       }
     }
   } else {
@@ -864,6 +869,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const int c_first = PARITY ? 0 : half;
         const u32 t_acc = lane_base + acc * TILE_N;
         u32 va[32], vb[32];
+        const bool early = TRIAGE && (p.debug & 128);      // triage (results invalid): hand the accumulator back BEFORE reading it
+        if (early) release_acc();
         tmem_ld32(t_acc + c_first * 32, va);
         tmem_ld32(t_acc + (c_first + C_STEP) * 32, vb);
 #pragma unroll 1
@@ -871,7 +878,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           const bool last = c + 2 * C_STEP >= N_CHUNKS;
           refresh_bound(c);
           tmem_wait_ld();
-          if (last) release_acc();
+          if (last && !early) release_acc();
           filter_chunk(c, va);
           if (!last) tmem_ld32(t_acc + (c + 2 * C_STEP) * 32, va);
           refresh_bound(c + C_STEP);
