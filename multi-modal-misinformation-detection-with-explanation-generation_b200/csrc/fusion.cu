@@ -4,21 +4,22 @@
 // (fusion_verdict) and, with a modality mask, the fallback rule of :884-899.
 //
 // 28 B in / 12 B out and 4 864 flop per sample: neither roof is reachable; the point is
-// one launch instead of ~8 and no .item() syncs.  Weights (10 120 B) are staged once per
-// block into shared memory, transposed so lane j reads column j conflict-free; layer-2
-// inputs travel by warp shuffle, so no shared-memory round trip per sample.
+// one launch instead of ~8 and no .item() syncs.  The weights (10 120 B) live in device memory
+// TRANSPOSED (mmf_fusion_load does it once on the host), so that lane j reads column j of every
+// layer with coalesced 128-byte loads straight into REGISTERS (81 per lane) -- no shared-memory
+// staging, no block barrier, and no shared-memory read per multiply in the sample loop; layer-2
+// inputs travel by warp shuffle.
 #include "common.cuh"
 
 namespace mmf {
 
-struct FusionSmem {
-  float w0t[5][64];    // w0t[i][j] = W0[j][i]
-  float b0[64];
-  float w3t[64][32];   // w3t[i][j] = W3[j][i]
-  float b3[32];
-  float w5[2][32];
-  float b5[2];
-};
+// device layout of the parameters (floats): lane j's column of every layer is contiguous across lanes
+constexpr int FP_W0T = 0;        // [5][64]   w0t[i][j] = W0[j][i]
+constexpr int FP_B0 = 320;       // [64]
+constexpr int FP_W3T = 384;      // [64][32]  w3t[i][j] = W3[j][i]
+constexpr int FP_B3 = 2432;      // [32]
+constexpr int FP_W5 = 2464;      // [2][32]
+constexpr int FP_B5 = 2528;      // [2]
 
 // ASSEMBLE: the fusion inputs are built here as well (analyze()'s score assembly, misinfo_forensics.py:794-809):
 // x[s] = [ai, misinfo, deepfake, clip_sim, vault_disc] from head (n,3), sim (n), disc (n) with the scores of a skipped
@@ -32,17 +33,16 @@ __global__ void __launch_bounds__(256) fusion_judge_kernel(const float* __restri
                                                            float* __restrict__ out_conf,
                                                            const float* __restrict__ head, float* __restrict__ sim,
                                                            float* __restrict__ disc, float* __restrict__ x_out) {
-  __shared__ FusionSmem w;
-  // params: [W0 (64,5) | b0 64 | W3 (32,64) | b3 32 | W5 (2,32) | b5 2]  (nn.Linear: weight (out,in))
-  for (int i = threadIdx.x; i < 320; i += blockDim.x) w.w0t[i % 5][i / 5] = params[i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) w.b0[i] = params[320 + i];
-  for (int i = threadIdx.x; i < 2048; i += blockDim.x) w.w3t[i % 64][i / 64] = params[384 + i];
-  for (int i = threadIdx.x; i < 32; i += blockDim.x) w.b3[i] = params[2432 + i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) w.w5[i / 32][i % 32] = params[2464 + i];
-  if (threadIdx.x < 2) w.b5[threadIdx.x] = params[2528 + threadIdx.x];
-  __syncthreads();
-
   const int lane = threadIdx.x & 31;
+  // this lane's columns of the three layers (independent loads, all in flight at once)
+  float w0a[5], w0b[5], w3[64];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { w0a[i] = __ldg(params + FP_W0T + i * 64 + lane); w0b[i] = __ldg(params + FP_W0T + i * 64 + 32 + lane); }
+#pragma unroll
+  for (int i = 0; i < 64; ++i) w3[i] = __ldg(params + FP_W3T + i * 32 + lane);
+  const float b0a = __ldg(params + FP_B0 + lane), b0b = __ldg(params + FP_B0 + 32 + lane), b3 = __ldg(params + FP_B3 + lane);
+  const float w5a = __ldg(params + FP_W5 + lane), w5b = __ldg(params + FP_W5 + 32 + lane);
+  const float b5a = __ldg(params + FP_B5), b5b = __ldg(params + FP_B5 + 1);
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long s = (((long long)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; s < n; s += warps) {
     const int mod = modality ? modality[s] : 3;
@@ -63,22 +63,22 @@ __global__ void __launch_bounds__(256) fusion_judge_kernel(const float* __restri
     for (int i = 0; i < 5; ++i) xi[i] = __shfl_sync(FULL, xl, i);
     float real, fake;
     if (mod == 3) {                                   // warp-uniform: one sample per warp
-      float h1a = w.b0[lane], h1b = w.b0[lane + 32];
+      float h1a = b0a, h1b = b0b;
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        h1a = fmaf(w.w0t[i][lane], xi[i], h1a);
-        h1b = fmaf(w.w0t[i][lane + 32], xi[i], h1b);
+        h1a = fmaf(w0a[i], xi[i], h1a);
+        h1b = fmaf(w0b[i], xi[i], h1b);
       }
       h1a = fmaxf(h1a, 0.f);
       h1b = fmaxf(h1b, 0.f);
-      float h2 = w.b3[lane];
+      float h2 = b3;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h2 = fmaf(w.w3t[i][lane], __shfl_sync(FULL, h1a, i), h2);
+      for (int i = 0; i < 32; ++i) h2 = fmaf(w3[i], __shfl_sync(FULL, h1a, i), h2);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) h2 = fmaf(w.w3t[32 + i][lane], __shfl_sync(FULL, h1b, i), h2);
+      for (int i = 0; i < 32; ++i) h2 = fmaf(w3[32 + i], __shfl_sync(FULL, h1b, i), h2);
       h2 = fmaxf(h2, 0.f);
-      const float l0 = warp_sum(w.w5[0][lane] * h2) + w.b5[0];
-      const float l1 = warp_sum(w.w5[1][lane] * h2) + w.b5[1];
+      const float l0 = warp_sum(w5a * h2) + b5a;
+      const float l1 = warp_sum(w5b * h2) + b5b;
       const float m = fmaxf(l0, l1);                  // torch.softmax(dim=1), :598
       const float e0 = expf(l0 - m), e1 = expf(l1 - m);
       const float inv = 1.0f / (e0 + e1);
@@ -134,8 +134,16 @@ extern "C" int mmf_fusion_load(mmf_handle* h, const float* params_host) {
   if (!params_host) return mmf_set_error(h, MMF_ERR_BAD_ARG, "fusion_load: null params");
   MMF_CUDA_OK(h, cudaSetDevice(h->device));
   if (!h->fusion_params) MMF_CUDA_OK(h, cudaMalloc(&h->fusion_params, MMF_FUSION_PARAMS * sizeof(float)));
-  // synchronous on purpose: the trainer mutates the weights in place and calls this again
-  MMF_CUDA_OK(h, cudaMemcpy(h->fusion_params, params_host, MMF_FUSION_PARAMS * sizeof(float), cudaMemcpyHostToDevice));
+  // params_host: [W0 (64,5) | b0 64 | W3 (32,64) | b3 32 | W5 (2,32) | b5 2]  (nn.Linear: weight (out,in)); the device
+  // copy holds W0 and W3 transposed (see the FP_* offsets).  Synchronous on purpose: the trainer mutates the weights
+  // in place and calls this again.
+  float t[MMF_FUSION_PARAMS];
+  memcpy(t, params_host, sizeof t);
+  for (int j = 0; j < 64; ++j)
+    for (int i = 0; i < 5; ++i) t[mmf::FP_W0T + i * 64 + j] = params_host[j * 5 + i];
+  for (int j = 0; j < 32; ++j)
+    for (int i = 0; i < 64; ++i) t[mmf::FP_W3T + i * 32 + j] = params_host[384 + j * 64 + i];
+  MMF_CUDA_OK(h, cudaMemcpy(h->fusion_params, t, sizeof t, cudaMemcpyHostToDevice));
   h->fusion_loaded = true;
   return MMF_OK;
 }

@@ -769,7 +769,8 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           return mn;
         };
         u32 mn = pool_min();
-        if (__any_sync(0xFFFFFFFFu, mn == 0u && valid_q) && !(TRIAGE && (p.debug & 64))) {
+        // (a vault of a few tiles cannot fill top_k buckets with one seed per tile: it takes its few candidate events instead of the wait)
+        if (p.v_tiles >= 8 * k && __any_sync(0xFFFFFFFFu, mn == 0u && valid_q) && !(TRIAGE && (p.debug & 64))) {
           float best = -INFINITY;
           int bj = 0;
 #pragma unroll 1
@@ -1207,18 +1208,22 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
     a = warp_sum(a);
     return pack_key(a * MMF_SPLIT_INV_SCALE, row);
   };
-  for (u32 i = warp; i < n_band; i += 16) {                      // two rows in flight per warp
-    const bool two = i + 8 < n_band;                             // (warp-uniform)
-    const u32 row0 = (u32)staging[i], row1 = two ? (u32)staging[i + 8] : row0;
-    uint4 ld0[4], ld1[4];
-    load_row(row0, ld0);
-    if (two) load_row(row1, ld1);
-    const u64 e0 = exact_key(row0, ld0);
-    const u64 e1 = two ? exact_key(row1, ld1) : 0ull;
-    __syncwarp();
-    if (lane == 0) {
-      staging[i] = e0;
-      if (two) staging[i + 8] = e1;
+  for (u32 base = warp; base < n_band; base += 32) {             // up to four rows in flight per warp: one HBM round trip
+    uint4 ld[4][4];                                              // for the usual band of 2-3 dozen rows
+    u32 row[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32 i = base + 8 * j;                                // (warp-uniform)
+      row[j] = i < n_band ? (u32)staging[i] : 0u;
+      if (i < n_band) load_row(row[j], ld[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32 i = base + 8 * j;
+      if (i < n_band) {
+        const u64 e = exact_key(row[j], ld[j]);
+        if (lane == 0) staging[i] = e;
+      }
     }
   }
   __syncthreads();
