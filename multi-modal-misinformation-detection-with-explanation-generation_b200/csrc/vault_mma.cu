@@ -1075,42 +1075,46 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
   const int qg = blockIdx.x;
   if (p.g_tau[qg] == 0xFFFFFFFFu) {                  // NaN query (block-uniform): the top_k highest row ids, NaN keys
-    if (!PUSH) { nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc); return; }
-    for (int i = threadIdx.x; i < p.top_k; i += blockDim.x)
-      sel.win[i] = i < p.n_rows ? ((0xFFFFFFFFull << 32) | (p.row_base + (u32)(p.n_rows - 1 - i))) : 0ull;
-    __syncthreads();
+    if constexpr (!PUSH) {
+      nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc);
+      return;
+    } else {
+      for (int i = threadIdx.x; i < p.top_k; i += blockDim.x)
+        sel.win[i] = i < p.n_rows ? ((0xFFFFFFFFull << 32) | (p.row_base + (u32)(p.n_rows - 1 - i))) : 0ull;
+      __syncthreads();
+    }
   } else {
     const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
     const u64 min_key = (u64)published_bound(p, qg) << 32;
     const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
     select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
   }
-  if (!PUSH) {
+  if constexpr (!PUSH) {
     write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
                        out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
                        out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
                        threshold);
-    return;
+  } else {
+    // sel.win[0..top_k): this query's winners, sorted (0 = empty).  Push them to every rank.
+    for (int i = threadIdx.x; i < p.top_k * px.world; i += blockDim.x) {
+      const int rr = i / p.top_k, j = i - rr * p.top_k;
+      const int peer = (px.rank + rr) % px.world;                  // own copy first, then round the ring
+      reinterpret_cast<u64*>(px.base[peer] + px.slot_off)[(long long)qg * p.top_k + j] = sel.win[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const u32 ticket = atomicAdd(px.done, 1u);
+      last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *px.done = 0;
+    __threadfence_system();
+    if ((int)threadIdx.x < px.world)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<u32*>(px.base[threadIdx.x]) +
+                                                              px.parity * MMF_XCHG_MAX_WORLD + px.rank), "r"(px.epoch) : "memory");
   }
-  // sel.win[0..top_k): this query's winners, sorted (0 = empty).  Push them to every rank.
-  for (int i = threadIdx.x; i < p.top_k * px.world; i += blockDim.x) {
-    const int rr = i / p.top_k, j = i - rr * p.top_k;
-    const int peer = (px.rank + rr) % px.world;                  // own copy first, then round the ring
-    reinterpret_cast<u64*>(px.base[peer] + px.slot_off)[(long long)qg * p.top_k + j] = sel.win[j];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const u32 ticket = atomicAdd(px.done, 1u);
-    last = ticket == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (!last) return;
-  if (threadIdx.x == 0) *px.done = 0;
-  __threadfence_system();
-  if ((int)threadIdx.x < px.world)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<u32*>(px.base[threadIdx.x]) +
-                                                            px.parity * MMF_XCHG_MAX_WORLD + px.rank), "r"(px.epoch) : "memory");
 }
 
 // Screened search, second half (VAR_SCREEN): one block per query.
