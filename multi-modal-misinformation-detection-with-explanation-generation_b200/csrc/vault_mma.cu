@@ -771,8 +771,18 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         u32 mn = pool_min();
         // (a vault of a few tiles cannot fill top_k buckets with one seed per tile: it takes its few candidate events instead of the wait)
         if (p.v_tiles >= 8 * k && __any_sync(0xFFFFFFFFu, mn == 0u && valid_q) && !(TRIAGE && (p.debug & 64))) {
+          // one seed per thread when the whole grid works on this query (C2: 74 pairs), one per 32-row chunk when only a
+          // few pairs do (1 000 queries = 4 groups of 18 pairs: 18 seeds cannot tell much about 10 buckets)
+          const bool seed_chunks = n_pairs < 64 * p.qtp;
           float best = -INFINITY;
           int bj = 0;
+          auto publish = [&]() {
+            if (valid_q && best > -INFINITY) {
+              const u32 ub = __float_as_uint((SPLIT || SCREEN) ? best * p.inv_scale : best);
+              const u32 row = row_id0 + bj;
+              atomicMax(pool + pool_bucket(row, (u32)k), ub ^ ((u32)((int)ub >> 31) | 0x80000000u));
+            }
+          };
 #pragma unroll 1
           for (int c = PARITY ? 0 : half; c < TILE_N / 32; c += PARITY ? 1 : 2) {
             u32 v[32];
@@ -783,12 +793,9 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
               const float a = (partial && c * 32 + j >= n_cols) ? -INFINITY : __uint_as_float(v[j]);
               if (a > best) { best = a; bj = c * 32 + j; }
             }
+            if (seed_chunks) { publish(); best = -INFINITY; }
           }
-          if (valid_q && best > -INFINITY) {       // ONE atomic per thread: 10 words per query take the seeds of the whole grid
-            const u32 ub = __float_as_uint((SPLIT || SCREEN) ? best * p.inv_scale : best);
-            const u32 row = row_id0 + bj;
-            atomicMax(pool + pool_bucket(row, (u32)k), ub ^ ((u32)((int)ub >> 31) | 0x80000000u));
-          }
+          if (!seed_chunks) publish();
           const long long t_end = clock64() + 20000;
           for (;;) {
             mn = pool_min();
@@ -1131,8 +1138,10 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
 // The staging bound is the better of g_tau (the best per-list k-th best) and the minimum over the bucket pool (a
 // grid-wide bound near rank 54 for top_k = 10): with g_tau alone ~700 candidates per query were staged and the
 // selection ran 8 radix passes; with the pool a few dozen are, and rank-by-counting does it in two barriers.
-template <int KPL, int CG>
-__global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int n_pairs, double threshold,
+// ROWS: vault rows in flight per warp while re-scoring -- 4 when the grid is at most two waves of blocks (latency is what
+// counts: C2, 256 queries), 2 otherwise (64 registers instead of 109: twice the blocks per SM; C1, 1 000 queries).
+template <int KPL, int CG, int ROWS>
+__global__ void __launch_bounds__(256, ROWS == 2 ? 4 : 2) mma_rerank_kernel(const MmaParams p, int n_pairs, double threshold,
                                                          const uint4* __restrict__ vault, float* out_scores,
                                                          long long* out_rows, u64* out_packed, float* out_disc) {
   constexpr int STAGING = 4096;
@@ -1163,6 +1172,9 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
   const u64 cut = kth ? (u64)okey(okey_inv((u32)(kth >> 32)) - p.margin) << 32 : 0ull;
   __syncthreads();
 
+  if (TRIAGE && (p.debug & 8) && tid == 0 && (qg & 127) == 0)
+    printf("[mmf debug] rerank query %d: %d list slots, %u candidates staged, bound %.4f, approximate k-th best %.4f\n", qg, n_slots,
+           n_staged, g ? okey_inv(g) : 0.f, kth ? okey_inv((u32)(kth >> 32)) : 0.f);
   // Compact the candidates inside the band to the front of the staging array (in place, 256 at a time: a round's
   // reads are done before its writes, which land below the round's end), so that the 8 warps share the rows to
   // re-score evenly -- each row is a 2 KB read from HBM, latency-bound.
@@ -1212,17 +1224,17 @@ __global__ void __launch_bounds__(256) mma_rerank_kernel(const MmaParams p, int 
     a = warp_sum(a);
     return pack_key(a * MMF_SPLIT_INV_SCALE, row);
   };
-  for (u32 base = warp; base < n_band; base += 32) {             // up to four rows in flight per warp: one HBM round trip
-    uint4 ld[4][4];                                              // for the usual band of 2-3 dozen rows
-    u32 row[4];
+  for (u32 base = warp; base < n_band; base += 8 * ROWS) {       // up to ROWS rows in flight per warp: with 4, one HBM round
+    uint4 ld[ROWS][4];                                           // trip for the usual band of 2-3 dozen rows
+    u32 row[ROWS];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < ROWS; ++j) {
       const u32 i = base + 8 * j;                                // (warp-uniform)
       row[j] = i < n_band ? (u32)staging[i] : 0u;
       if (i < n_band) load_row(row[j], ld[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < ROWS; ++j) {
       const u32 i = base + 8 * j;
       if (i < n_band) {
         const u64 e = exact_key(row[j], ld[j]);
@@ -1439,8 +1451,12 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   h->launches++;
   mmf_push_ctx no_push = {};
   if constexpr ((VAR & VAR_SCREEN) != 0) {
-    mma_rerank_kernel<KPL, CG><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
-                                                             (long long*)out_rows, (u64*)out_packed, out_disc);
+    if (p.n_queries <= 4 * h->sm_count)
+      mma_rerank_kernel<KPL, CG, 4><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                                  (long long*)out_rows, (u64*)out_packed, out_disc);
+    else
+      mma_rerank_kernel<KPL, CG, 2><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
+                                                                  (long long*)out_rows, (u64*)out_packed, out_disc);
   } else if constexpr ((VAR & VAR_GUARD) != 0) {
     mma_merge_kernel<KPL, CG, true, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
                                                                          (u64*)out_packed, out_disc, no_push);

@@ -176,6 +176,13 @@ int main(int argc, char** argv) {
     fill_rows<<<(4096 * 512 + 255) / 256, 256>>>(d_q, 4096, 12);
     CK(cudaDeviceSynchronize());
     MM(mmf_vault_load(H, d_vault, 1, 1000000, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    if (getenv("PROFILE_C1")) {      // the C1 shape instead: 1 000 queries x 100 000 rows
+      MM(mmf_vault_load(H, d_vault, 1, 100000, 512, MMF_F32, MMF_VAULT_FP32, 0));
+      search(1000, 10, MMF_ALGO_MMA);
+      printf("profile mode: C1 search done\n");
+      mmf_destroy(H);
+      return 0;
+    }
     search(256, 10, MMF_ALGO_MMA);
     search(1, 10, MMF_ALGO_STREAM);
     fill_rows<<<(unsigned)((1250000ll * 512 + 255) / 256), 256>>>(d_vault, 1250000, 21);
