@@ -29,6 +29,7 @@ renormalisation of the whole vault in NumPy) on the host cores, rank 0 only.
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -82,43 +83,68 @@ def ncu_traffic(summary):
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / power / throttle reasons UNDER THE LOAD of the timed steps.  nvidia-smi needs ~0.1 s to print its
+    first line and a C2 timed region lasts ~8 ms, so: the process is started before the warm-up, `window_start()` is
+    called right before the timed region, and `hold_load()` keeps launching the very same steps (untimed, after the
+    closing event) until the window is 0.5 s long.  Only lines stamped inside the window are kept."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MIN_WINDOW_S = 0.5
 
-    def __init__(self, index: int, period_ms: int = 50):
-        self.proc = None
+    def __init__(self, index: int, period_ms: int = 20):
+        self.proc, self.t0, self.t1, self.wall0, self.held = None, None, None, None, False
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
+    def window_start(self):
+        self.t0, self.wall0 = datetime.datetime.now(), time.perf_counter()
+
+    def hold_load(self, step, sync):
+        """keep the load of the timed region going until the sampling window is MIN_WINDOW_S long"""
+        if self.proc is None or self.wall0 is None:
+            return
+        self.held = True
+        while time.perf_counter() - self.wall0 < self.MIN_WINDOW_S:
+            for _ in range(8):
+                step()
+            sync()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        self.t1 = datetime.datetime.now()
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
         except Exception:
             self.proc.kill()
             out = ""
-        sm, mx, pw, reasons = [], [], [], set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
-                pw.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[1]), float(f[2]), float(f[3]), f[4:8]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        window = ("timed region + the same steps continued untimed to %.1f s" % self.MIN_WINDOW_S) if self.held else "timed region"
+        if not inside:                      # clock skew / no line in the window: say so instead of pretending
+            inside, window = rows, "whole sampler lifetime (no line was stamped inside the load window)"
+        sm, mx, pw, reasons = [r[1] for r in inside], [r[2] for r in inside], [r[3] for r in inside], set()
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "window": window, "reasons": sorted(reasons)}
 
 
 def host_info():
@@ -393,11 +419,13 @@ def run_replica(ctx, wl_name, wl, headline, algo="auto", rows_overridden=False, 
     assert torch.equal(vr3, out["vault_rows"]) and torch.equal(vs3, out["vault_scores"]) and torch.equal(probs3, out["probs"]), \
         f"{wl_name}: mmf_score_batch differs from cosine + search + verdict_assemble"
 
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         step_device()
     ctx.barrier()
     launches0 = eng.launch_count
-    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.window_start()
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     search_ev = []
     marks[0].record()
@@ -407,6 +435,8 @@ def run_replica(ctx, wl_name, wl, headline, algo="auto", rows_overridden=False, 
         marks[i + 1].record()
     ctx.barrier()
     launches = eng.launch_count - launches0
+    if sampler:
+        sampler.hold_load(step_device, torch.cuda.synchronize)
     step_ms = marks[0].elapsed_time(marks[-1]) / args.steps
     per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
     per_search = [a.elapsed_time(b) for a, b in search_ev]
@@ -557,10 +587,12 @@ def run_c4(ctx, wl, steps, warmup, rows_overridden=False):
             torch.cuda.empty_cache()
         assert exact, "c4: the row-sharded search differs from the unsharded one"
 
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     for _ in range(warmup):
         vault.search(q_dev, K)
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.window_start()
     l0, c0 = eng.launch_count, eng.collective_count
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
     marks[0].record()
@@ -720,10 +752,12 @@ def run_c5(ctx, batch=256, rows=1_000_000, top_k=5, steps=8, warmup=3, keep=None
         if ev:
             ev[2].record()
         return out
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
     for _ in range(warmup):
         step()
     ctx.barrier()
-    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    if sampler:
+        sampler.window_start()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
     for e in evs:
         out = step(e)
