@@ -127,7 +127,7 @@ extern "C" int mmf_create(int device_ordinal, mmf_handle** out) {
   }
   // the only place the environment is read: MMF_OPT_SCREEN, MMF_OPT_FUSED_PUSH, MMF_OPT_DEBUG, MMF_OPT_FORCE_CG,
   // MMF_OPT_FLAT_SCHEDULE (same names as mmf_set_option, upper case)
-  for (const char* name : {"screen", "fused_push", "debug", "force_cg", "flat_schedule", "epi_parity", "stream_tma"}) {
+  for (const char* name : {"screen", "fused_push", "debug", "force_cg", "flat_schedule", "epi_parity", "stream_tma", "lockstep"}) {
     char env[64] = "MMF_OPT_";
     size_t n = strlen(env);
     for (const char* c = name; *c && n + 1 < sizeof env; ++c) env[n++] = (char)toupper((unsigned char)*c);
@@ -148,6 +148,7 @@ extern "C" int mmf_set_option(mmf_handle* h, const char* name, int value) {
   else if (!strcmp(name, "force_cg")) o.force_cg = (value == 1 || value == 2) ? value : 0;
   else if (!strcmp(name, "flat_schedule")) o.flat_schedule = value != 0;
   else if (!strcmp(name, "epi_parity")) o.epi_parity = value < 0 ? -1 : (value != 0);
+  else if (!strcmp(name, "lockstep")) o.lockstep = value != 0;
   else if (!strcmp(name, "stream_tma")) o.stream_tma = value != 0;
   else return mmf_set_error(h, MMF_ERR_BAD_ARG, "set_option: unknown option '%s'", name);
   return MMF_OK;
@@ -162,6 +163,7 @@ extern "C" int mmf_get_option(const mmf_handle* h, const char* name, int* value)
   else if (!strcmp(name, "force_cg")) *value = o.force_cg;
   else if (!strcmp(name, "flat_schedule")) *value = o.flat_schedule;
   else if (!strcmp(name, "epi_parity")) *value = o.epi_parity;
+  else if (!strcmp(name, "lockstep")) *value = o.lockstep;
   else if (!strcmp(name, "stream_tma")) *value = o.stream_tma;
   else return MMF_ERR_BAD_ARG;
   return MMF_OK;

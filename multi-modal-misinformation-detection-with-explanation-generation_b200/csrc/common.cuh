@@ -88,6 +88,7 @@ struct mmf_options {
   int force_cg = 0;        // tcgen05 search: force 1 or 2 CTAs per MMA (0 = automatic)
   int flat_schedule = 0;   // tcgen05 search: plain flattened schedule instead of the L2-aware one
   int stream_tma = 1;      // streaming (batch-1) search: TMA-staged kernel (1) or the register-staged one (0)
+  int lockstep = 1;        // tcgen05 search with several query-tile groups: producers of a segment stay within 64 tiles of each other
   int epi_parity = -1;     // tcgen05 search, 1-plane kernels with top_k <= 16: epilogue warp sets alternate tiles (1), all warps
                            // work on every tile (0), or chosen by strip length (-1, default)
 };

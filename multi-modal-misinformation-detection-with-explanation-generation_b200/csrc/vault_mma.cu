@@ -121,6 +121,10 @@ struct MmaParams {
   int* ovf;                // screened search: set to 1 when a candidate band overflowed -> the guarded exact pass runs
   float margin;            // screened search: width of the candidate band in score units (2 x error bound)
   const float* qn;         // screened search: [q_pad][512] fp32 normalised queries (exact re-scoring)
+  // lock-step producers (qtp > 1): progress[pair] = vault tiles the pair's producer has requested; a producer does not run
+  // more than lockstep_w tiles ahead of the slowest pair of its segment (0 = off)
+  u32* progress;
+  int lockstep_w;
 };
 
 // Which tiles a pair works on.  A vault tile is wanted by every group of query tiles (qtp of them), and
@@ -520,7 +524,27 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
       int cur_tp = -1;
       int tp = sch.tp0, vt = sch.vt0;      // tp: index of the group of CG query tiles
       const u32 q_full_l = (CG == 2) ? mapa(smem_u32(q_full), 0) : smem_u32(q_full);
+      // Lock-step with the other pairs of the segment (they sweep the same vault tiles, each for its own group of query
+      // tiles): whoever fetches a tile first brings it into L2 for the others -- as long as they stay within an L2's worth
+      // of each other.  Candidate events make pairs drift apart (measured on 10 M rows: the vault was read 12x from
+      // DRAM), so the leader's producer publishes its position every 16 tiles and waits while it is more than
+      // lockstep_w tiles ahead of the slowest pair of its segment.  The slowest never waits, a finished pair publishes
+      // "infinity", and the wait is bounded, so a pair that is not running yet cannot hang the others.
+      const bool lockstep = leader && p.lockstep_w > 0 && p.qtp > 1 && pair < p.n_aligned;
+      volatile u32* seg_progress = p.progress + (pair / max(p.qtp, 1)) * p.qtp;
       for (int u = 0; u < sch.n_tiles; ++u, ++vt) {
+        if (lockstep && (u & 15) == 0) {
+          p.progress[pair] = (u32)u;
+          if (u >= p.lockstep_w) {
+            const long long t_end = clock64() + 400000;       // ~0.25 ms: far beyond any healthy drift
+            for (;;) {
+              u32 mn = 0xFFFFFFFFu;
+              for (int t = 0; t < p.qtp; ++t) mn = min(mn, seg_progress[t]);
+              if ((u32)u <= mn + (u32)p.lockstep_w || clock64() > t_end) break;
+              __nanosleep(500);
+            }
+          }
+        }
         if (vt == sch.v_hi) { vt = sch.v_lo; ++tp; }
         if (SPLIT && tp != cur_tp) {                  // new strip: (re)load this CTA's resident ql tile (plane 1)
           cur_tp = tp;
@@ -564,6 +588,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           }
         }
       }
+      if (lockstep) p.progress[pair] = 0x7FFFFFFFu;
     }
   } else if (warp == MMA_WARP) {
     // ===== MMA issuer (leader CTA only) =====
@@ -1513,7 +1538,8 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   const size_t off_tau = off_q + al((size_t)npl * p.q_pad * MMF_DIM * 2);
   const size_t off_pool = off_tau + al((size_t)p.q_pad * 4);
   const size_t off_cnt = off_pool + al((size_t)p.q_pad * MMF_MAX_TOP_K * 4);
-  const size_t off_flag = off_cnt + al((size_t)lists * 4);                 // contiguous with cand_cnt: cleared together
+  const size_t off_prog = off_cnt + al((size_t)lists * 4);                 // producers' progress words (lock-step), cleared with
+  const size_t off_flag = off_prog + 1024;                                 // cand_cnt: both are contiguous with it
   const size_t off_cnt2 = off_flag + (screen ? 1024 : 0);
   const size_t off_tau2 = off_cnt2 + (screen ? al((size_t)lists * 4) : 0);
   const size_t off_pool2 = off_tau2 + (screen ? al((size_t)p.q_pad * 4) : 0);
@@ -1530,6 +1556,9 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.pool = (u32*)(sc + off_pool);
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
   p.ovf = screen ? (int*)(sc + off_flag) : nullptr;
+  p.progress = (u32*)(sc + off_prog);
+  // window: a quarter of L2 per segment-and-then-some (a bf16 / fp16-hi tile is 128 KB); option "lockstep" = 0 turns it off
+  p.lockstep_w = h->opt.lockstep ? 64 : 0;
   p.margin = screen ? 2.0f * SCREEN_EPS : 0.f;
   p.qn = screen ? (const float*)(sc + off_qn) : nullptr;
 

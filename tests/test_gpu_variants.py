@@ -317,6 +317,24 @@ def test_options(eng):
         eng.set_option("no-such-switch", 1)
 
 
+def test_lockstep_producers_do_not_change_results(eng):
+    """option `lockstep` only paces the TMA producers of the tcgen05 search (several query-tile groups sweeping the same vault
+    tiles stay within an L2's worth of each other): same rows, same scores, on or off"""
+    n_rows, n_q = 300000, 1300                                       # 6 groups of 256 queries: a segment grid + leftover pairs
+    vault = synth.vault_rows(n_rows, seed=61)
+    q, _, _ = synth.queries(n_q, n_rows, seed=62, vault_seed=61)
+    eng.vault_load(vault, mode="bf16")
+    assert eng.get_option("lockstep") == 1 or DOUBLE
+    for k in (10, 100):
+        eng.set_option("lockstep", 1)
+        on = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+        eng.set_option("lockstep", 0)
+        off = [npy(t) for t in eng.vault_search(q, k, algo="mma")]
+        eng.set_option("lockstep", 1)
+        for a, b, what in zip(on, off, ("scores", "rows", "discrepancy")):
+            assert np.array_equal(a, b, equal_nan=True), f"top-{k}: {what} differ with lock-step producers on / off"
+
+
 def test_score_batch_entries_agree(eng):
     """Engine.score_batch (mmf_score_batch: one asynchronous call, device tensors) == Engine.score_batch_host (host buffers)
     == submit / collect with two batches in flight == cosine + search + verdict_assemble, with and without a modality mask"""

@@ -176,6 +176,16 @@ int main(int argc, char** argv) {
     fill_rows<<<(4096 * 512 + 255) / 256, 256>>>(d_q, 4096, 12);
     CK(cudaDeviceSynchronize());
     MM(mmf_vault_load(H, d_vault, 1, 1000000, 512, MMF_F32, MMF_VAULT_FP32, 0));
+    if (rows_bf16_a > 1250000) {     // `profile <rows>`: the one-GPU C4 shape, lock-step producers on, then off (for ncu's DRAM counters)
+      fill_rows<<<(unsigned)((rows_bf16_a * 512 + 255) / 256), 256>>>(d_vault, rows_bf16_a, 21);
+      CK(cudaDeviceSynchronize());
+      MM(mmf_vault_load(H, d_vault, 1, rows_bf16_a, 512, MMF_F32, MMF_VAULT_BF16, 0));
+      opt("lockstep", 1); search(4096, 100, MMF_ALGO_MMA);
+      opt("lockstep", 0); search(4096, 100, MMF_ALGO_MMA);
+      printf("profile mode: 2 searches of 4096 x %lld bf16 rows done\n", rows_bf16_a);
+      mmf_destroy(H);
+      return 0;
+    }
     if (getenv("PROFILE_C1")) {      // the C1 shape instead: 1 000 queries x 100 000 rows
       MM(mmf_vault_load(H, d_vault, 1, 100000, 512, MMF_F32, MMF_VAULT_FP32, 0));
       search(1000, 10, MMF_ALGO_MMA);
@@ -237,6 +247,23 @@ int main(int argc, char** argv) {
       std::vector<float> v = t[a];
       for (size_t i = 0; i < v.size(); ++i) for (size_t j = i + 1; j < v.size(); ++j) if (v[j] < v[i]) { float x = v[i]; v[i] = v[j]; v[j] = x; }
       printf("  bf16 4096 x 1.25M top-10: %-36s min %.4f  median %.4f ms\n", arms[a].name, v[0], v[v.size() / 2]);
+    }
+    if (rows_bf16_a > 1250000) {      // `tune <rows>`: the one-GPU C4 shape (4 096 queries, top-100), lock-step producers on / off
+      opt("epi_parity", -1);
+      fill_rows<<<(unsigned)((rows_bf16_a * 512 + 255) / 256), 256>>>(d_vault, rows_bf16_a, 21);
+      CK(cudaDeviceSynchronize());
+      MM(mmf_vault_load(H, d_vault, 1, rows_bf16_a, 512, MMF_F32, MMF_VAULT_BF16, 0));
+      std::vector<float> t_on, t_off;
+      Result r_on, r_off;
+      for (int r = 0; r < 3; ++r) {
+        float ms = 0;
+        opt("lockstep", 1); r_on = search(4096, 100, MMF_ALGO_MMA, &ms, 2); t_on.push_back(ms);
+        opt("lockstep", 0); r_off = search(4096, 100, MMF_ALGO_MMA, &ms, 2); t_off.push_back(ms);
+      }
+      opt("lockstep", 1);
+      fails += !same(r_on, r_off, 4096, 100, "lock-step producers on vs off");
+      printf("  bf16 4096 x %lld top-100: lock-step producers on  %.3f %.3f %.3f ms\n", rows_bf16_a, t_on[0], t_on[1], t_on[2]);
+      printf("  bf16 4096 x %lld top-100: lock-step producers off %.3f %.3f %.3f ms\n", rows_bf16_a, t_off[0], t_off[1], t_off[2]);
     }
     printf("tune: %d mismatches\n", fails);
     mmf_destroy(H);
