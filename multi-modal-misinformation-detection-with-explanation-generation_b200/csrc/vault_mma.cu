@@ -861,29 +861,52 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
         const float m8 = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
         if (TRIAGE && (p.debug & 16)) { if (m8 == 12345.678f) cnt = 1; return; }      // triage: tcgen05.ld + max tree only
         if (!(m8 < MMF_TAU_F) && valid_q && !(TRIAGE && (p.debug & 32) && u - strip_u0 >= 2)) {   // triage bit 5: no events after the warm-up tiles
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (!(mx[i] < MMF_TAU_F)) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(v[4 * i + e]);
-                const int col = c * 32 + 4 * i + e;
-                if (!(a < MMF_TAU_F) && (!partial || col < n_cols)) {
-                  // candidate event: keep it short (a lone warp retires ~1 instruction per 4-5 clk).  The key
-                  // is the order-preserving transform without okey()'s NaN / -0.0 canonicalisation: tensor-
-                  // core NaNs are positive (they still rank first) and -0.0 only matters for tie order.
-                  const u32 ub = __float_as_uint((SPLIT || SCREEN) ? a * p.inv_scale : a);
-                  const u32 key = ub ^ ((u32)((int)ub >> 31) | 0x80000000u);
-                  const u32 row = row_id0 + col;
-                  buf[cnt++] = ((u64)key << 32) | row;
-                  if (HIST) {
-                    const int bin = hist_bin(ub);
-                    if (bin > 0) atomicAdd(pool + bin, 1u);     // bin 0 (score < 2^-7) carries no bound
-                  } else {
-                    atomicMax(pool + pool_bucket(row, (u32)k), key);
-                  }
-                }
+          // Candidate events: rare per chunk, but a lone warp pays ~15 clk for every branch it takes, and the obvious
+          // form -- 8 group tests, 4 element tests per hit group, the event body unrolled 32x -- was a dozen branches
+          // and ~300 clk per event.  Here: a bit mask of the groups of 4 that hold a candidate (no
+          // branches), one indexed jump per hit group to fetch its 4 values, and ONE copy of the event body, fed with
+          // the group's maximum (a candidate for sure); the group's other elements are looked at only when more than
+          // one of them passes.
+          auto emit = [&](float a, int col) {
+            if (!partial || col < n_cols) {
+              // the key is the order-preserving transform without okey()'s NaN / -0.0 canonicalisation: tensor-core
+              // NaNs are positive (they still rank first) and -0.0 only matters for tie order
+              const u32 ub = __float_as_uint((SPLIT || SCREEN) ? a * p.inv_scale : a);
+              const u32 key = ub ^ ((u32)((int)ub >> 31) | 0x80000000u);
+              const u32 row = row_id0 + col;
+              buf[cnt++] = ((u64)key << 32) | row;
+              if (HIST) {
+                const int bin = hist_bin(ub);
+                if (bin > 0) atomicAdd(pool + bin, 1u);     // bin 0 (score < 2^-7) carries no bound
+              } else {
+                atomicMax(pool + pool_bucket(row, (u32)k), key);
               }
+            }
+          };
+          const float tau_f = MMF_TAU_F;
+          u32 gm = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gm |= (!(mx[i] < tau_f) ? 1u : 0u) << i;
+#pragma unroll 1
+          while (gm) {
+            const int i = __ffs(gm) - 1;
+            gm &= gm - 1;
+            float a0, a1, a2, a3;
+            switch (i) {
+#define MMF_GROUP(I_) case I_: a0 = __uint_as_float(v[4 * I_]); a1 = __uint_as_float(v[4 * I_ + 1]); \
+                               a2 = __uint_as_float(v[4 * I_ + 2]); a3 = __uint_as_float(v[4 * I_ + 3]); break;
+              MMF_GROUP(0) MMF_GROUP(1) MMF_GROUP(2) MMF_GROUP(3) MMF_GROUP(4) MMF_GROUP(5) MMF_GROUP(6)
+              default: a0 = __uint_as_float(v[28]); a1 = __uint_as_float(v[29]); a2 = __uint_as_float(v[30]); a3 = __uint_as_float(v[31]); break;
+#undef MMF_GROUP
+            }
+            const int cb = c * 32 + 4 * i;
+            const bool h0 = !(a0 < tau_f), h1 = !(a1 < tau_f), h2 = !(a2 < tau_f), h3 = !(a3 < tau_f);
+            const int e = h0 ? 0 : h1 ? 1 : h2 ? 2 : 3;                       // first candidate of the group (there is one)
+            emit(h0 ? a0 : h1 ? a1 : h2 ? a2 : a3, cb + e);
+            if ((int)h0 + (int)h1 + (int)h2 + (int)h3 > 1) {                  // rare: the others
+              if (h1 && e < 1) emit(a1, cb + 1);
+              if (h2 && e < 2) emit(a2, cb + 2);
+              if (h3 && e < 3) emit(a3, cb + 3);
             }
           }
         }
