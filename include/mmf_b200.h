@@ -247,7 +247,8 @@ int mmf_score_batch_collect(mmf_handle* h, int slot, float* out_clip_similarity,
  * (MMF_OPT_<NAME>), never on the search path.  Names: "screen" (fp32-exact vaults, top_k <= 16: 1 = screened
  * search, default; 0 = 3-pass kernel), "fused_push" (peer-memory exchange: the search pushes its winners itself,
  * default 1), "debug" (tcgen05 search triage bits), "force_cg" (1 / 2 CTAs per MMA, 0 = automatic),
- * "flat_schedule", "epi_parity". */
+ * "flat_schedule", "epi_parity" (-1 = by strip length), "stream_tma" (1 = TMA-staged streaming kernel, default),
+ * "lockstep" (1 = producers of the tcgen05 search that sweep the same vault tiles pace each other, default). */
 int mmf_set_option(mmf_handle* h, const char* name, int value);
 int mmf_get_option(const mmf_handle* h, const char* name, int* value);
 
