@@ -93,6 +93,7 @@ class ClockSampler:
 
     def __init__(self, index: int, period_ms: int = 20):
         self.proc, self.t0, self.t1, self.wall0, self.held = None, None, None, None, False
+        self.spawned = time.perf_counter()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", str(period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -107,7 +108,8 @@ class ClockSampler:
         if self.proc is None or self.wall0 is None:
             return
         self.held = True
-        while time.perf_counter() - self.wall0 < self.MIN_WINDOW_S:
+        # (nvidia-smi prints its first line some tenths of a second after it was spawned: the window also lasts until then)
+        while time.perf_counter() - self.wall0 < self.MIN_WINDOW_S or time.perf_counter() - self.spawned < 2 * self.MIN_WINDOW_S:
             for _ in range(8):
                 step()
             sync()
