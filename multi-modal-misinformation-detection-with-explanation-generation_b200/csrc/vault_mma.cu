@@ -98,6 +98,7 @@ constexpr int EPI_WARPS = 8;          // 2 per TMEM lane quarter: a lone warp pe
 constexpr int PRODUCER_WARP = EPI_WARPS;      // warps 0-7: epilogue (warp%4 = TMEM lane quarter), 8: TMA producer,
 constexpr int MMA_WARP = EPI_WARPS + 1;       // 9: MMA issuer -- the highest warp id on its scheduler, so it wins arbitration
 constexpr int MMA_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int MERGE_MAX_SLOTS_BYTES = 4 * 160 * 4;     // (MERGE_MAX_SLOTS ints, see the tail kernels)
 
 struct MmaParams {
   int n_queries;           // valid queries
@@ -125,6 +126,10 @@ struct MmaParams {
   // more than lockstep_w tiles ahead of the slowest pair of its segment (0 = off)
   u32* progress;
   int lockstep_w;
+  // guarded exact pass (VAR_GUARD) only: it merges its own candidate lists behind a grid barrier, so that the usual case
+  // (no band overflowed) costs ONE launch that returns at once instead of two
+  u32* grid_sync;          // zeroed by the preparation kernel
+  float* g_scores; long long* g_rows; u64* g_packed; float* g_disc; double g_threshold;
 };
 
 // Which tiles a pair works on.  A vault tile is wanted by every group of query tiles (qtp of them), and
@@ -400,7 +405,7 @@ __device__ __forceinline__ void prep_query_row(const float* __restrict__ q, int 
 // The ONE preparation launch of a search: normalised query planes, cleared bounds, cleared candidate counters
 // (zero[0..zero_n): the counters of this search and, for the screened search, the overflow flag and the counters
 // of the guarded pass) and -- screened search only -- a second set of bounds for the guarded exact pass (bucket
-// pool, top_k <= 16), so that a screened search is 5 launches and no memset.
+// pool, top_k <= 16), so that a screened search is 4 launches and no memset.
 __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __restrict__ q, int n_queries, int q_pad,
                                                              int split, void* __restrict__ planes,
                                                              u32* __restrict__ g_tau, u32* __restrict__ pool,
@@ -444,6 +449,10 @@ __global__ void __launch_bounds__(256) mma_query_prep_kernel(const float* __rest
 // 3-pass kernel redoes the batch.
 // VAR_PARITY (KR > 0 only): how the 8 epilogue warps share the accumulators, see PARITY below.
 constexpr int VAR_SCREEN = 2, VAR_GUARD = 4, VAR_PARITY = 8;
+struct SelectSmem;
+template <int KPL, int CG>
+__device__ void merge_query(const MmaParams& p, int n_pairs, int qg, double threshold, float* out_scores, long long* out_rows,
+                            u64* out_packed, float* out_disc, SelectSmem& sel, u64* staging, int* slots, int* n_slots);
 template <bool SPLIT, int KPL, int CG, int KR, int VAR = 0>
 __global__ void __launch_bounds__(MMA_THREADS, 1)
 vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -1018,6 +1027,29 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
     if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
+  if constexpr (GUARD) {
+    // The rare path finishes inside this launch: once every block of the grid has written its lists (one block per SM,
+    // all resident: a counter in global memory is a grid barrier), the blocks share the queries and merge them, with the
+    // staging areas of the merge carved from the now idle stage ring.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicAdd(p.grid_sync, 1u);
+      while (*reinterpret_cast<volatile u32*>(p.grid_sync) < gridDim.x) __nanosleep(200);
+      __threadfence();
+    }
+    __syncthreads();
+    static_assert(sizeof(SelectSmem) <= 16384 && mma_smem_bytes(SPLIT, CG) >= 16384 + 4096 * 8 + MERGE_MAX_SLOTS_BYTES + 16,
+                  "the merge's shared memory must fit the stage ring");
+    SelectSmem& sel = *reinterpret_cast<SelectSmem*>(smem);
+    u64* staging = reinterpret_cast<u64*>(smem + 16384);
+    int* slots = reinterpret_cast<int*>(smem + 16384 + 4096 * 8);
+    int* n_slots = reinterpret_cast<int*>(smem + 16384 + 4096 * 8 + MERGE_MAX_SLOTS_BYTES);
+    for (int qg = blockIdx.x; qg < p.n_queries; qg += gridDim.x) {
+      merge_query<KPL, CG>(p, n_pairs, qg, p.g_threshold, p.g_scores, p.g_rows, p.g_packed, p.g_disc, sel, staging, slots, n_slots);
+      __syncthreads();
+    }
+  }
 }
 
 // Slots (strip * 2 + column half) of the candidate lists that cover query-tile group `tp`: every pair whose
@@ -1025,6 +1057,7 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
 // passed) on entry; may end up > MERGE_MAX_SLOTS, only the first MERGE_MAX_SLOTS entries are written.  The order of
 // the slots depends on the schedule of the atomics; the selection that follows does not.
 constexpr int MERGE_MAX_SLOTS = 4 * 160;
+static_assert(MERGE_MAX_SLOTS * 4 == MERGE_MAX_SLOTS_BYTES, "keep in sync");
 __device__ __forceinline__ void gather_slots_par(const MmaParams& p, int n_pairs, int tp, int* slots, int* n_slots) {
   for (int c = threadIdx.x; c < n_pairs; c += blockDim.x) {
     const PairSchedule sc = pair_schedule(p, c, n_pairs);
@@ -1118,7 +1151,24 @@ __device__ __forceinline__ void select_staged(const CandidateLists& src, u32 n, 
 // PUSH: row-sharded search over peer memory (exchange.cu): instead of writing outputs, the top_k winners go straight
 // from shared memory into slot [rank] of EVERY rank's gather buffer (the own one included) -- the NVLink transfer of
 // query i overlaps the selection of the other queries -- and the last block publishes this rank's epoch flag.
-template <int KPL, int CG, bool GUARD, bool PUSH>
+// One query's candidate lists -> its sorted top_k in the caller's outputs (all threads of the block call it; any block size).
+template <int KPL, int CG>
+__device__ void merge_query(const MmaParams& p, int n_pairs, int qg, double threshold, float* out_scores, long long* out_rows,
+                            u64* out_packed, float* out_disc, SelectSmem& sel, u64* staging, int* slots, int* n_slots) {
+  if (p.g_tau[qg] == 0xFFFFFFFFu) {                  // NaN query (block-uniform): the top_k highest row ids, NaN keys
+    nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc);
+    return;
+  }
+  const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, n_slots);
+  const u64 min_key = (u64)published_bound(p, qg) << 32;
+  const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
+  select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
+  write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
+                     out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
+                     out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr, threshold);
+}
+
+template <int KPL, int CG, bool PUSH>
 __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n_pairs, double threshold,
                                                         float* out_scores, long long* out_rows, u64* out_packed,
                                                         float* out_disc, const mmf_push_ctx px) {
@@ -1127,29 +1177,20 @@ __global__ void __launch_bounds__(256) mma_merge_kernel(const MmaParams p, int n
   __shared__ int slots[MERGE_MAX_SLOTS];  // (strip, half) slots holding lists of this query's tile group
   __shared__ int n_slots;
   __shared__ bool last;
-  if (GUARD && *reinterpret_cast<volatile int*>(p.ovf) == 0) return;
   const int qg = blockIdx.x;
-  if (p.g_tau[qg] == 0xFFFFFFFFu) {                  // NaN query (block-uniform): the top_k highest row ids, NaN keys
-    if constexpr (!PUSH) {
-      nan_query_outputs(p, qg, out_scores, out_rows, out_packed, out_disc);
-      return;
-    } else {
+  if constexpr (!PUSH) {
+    merge_query<KPL, CG>(p, n_pairs, qg, threshold, out_scores, out_rows, out_packed, out_disc, sel, staging, slots, &n_slots);
+  } else {
+    if (p.g_tau[qg] == 0xFFFFFFFFu) {                // NaN query (block-uniform): the top_k highest row ids, NaN keys
       for (int i = threadIdx.x; i < p.top_k; i += blockDim.x)
         sel.win[i] = i < p.n_rows ? ((0xFFFFFFFFull << 32) | (p.row_base + (u32)(p.n_rows - 1 - i))) : 0ull;
       __syncthreads();
+    } else {
+      const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
+      const u64 min_key = (u64)published_bound(p, qg) << 32;
+      const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
+      select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
     }
-  } else {
-    const CandidateLists src = lists_of_query<KPL, CG>(p, n_pairs, qg, slots, &n_slots);
-    const u64 min_key = (u64)published_bound(p, qg) << 32;
-    const u32 n = stage_candidates(src, sel, staging, 4096, min_key);
-    select_staged(src, n, staging, 4096, min_key, p.top_k, sel);
-  }
-  if constexpr (!PUSH) {
-    write_topk_outputs(sel, p.top_k, out_scores ? out_scores + (long long)qg * p.top_k : nullptr,
-                       out_rows ? out_rows + (long long)qg * p.top_k : nullptr,
-                       out_packed ? out_packed + (long long)qg * p.top_k : nullptr, out_disc ? out_disc + qg : nullptr,
-                       threshold);
-  } else {
     // sel.win[0..top_k): this query's winners, sorted (0 = empty).  Push them to every rank.
     for (int i = threadIdx.x; i < p.top_k * px.world; i += blockDim.x) {
       const int rr = i / p.top_k, j = i - rr * p.top_k;
@@ -1495,7 +1536,12 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], p));
+  MmaParams pk = p;
+  if constexpr ((VAR & VAR_GUARD) != 0) {       // the guarded kernel writes the search's outputs itself
+    pk.g_scores = out_scores; pk.g_rows = (long long*)out_rows; pk.g_packed = (u64*)out_packed; pk.g_disc = out_disc;
+    pk.g_threshold = threshold;
+  }
+  MMF_CUDA_OK(h, cudaLaunchKernelEx(&cfg, kern, tm_q, s->tm_vault[CG - 1], pk));
   h->launches++;
   mmf_push_ctx no_push = {};
   if constexpr ((VAR & VAR_SCREEN) != 0) {
@@ -1506,15 +1552,14 @@ static int launch_mma(mmf_handle* h, MmaState* s, const CUtensorMap& tm_q, const
       mma_rerank_kernel<KPL, CG, 2><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, (const uint4*)h->vault, out_scores,
                                                                   (long long*)out_rows, (u64*)out_packed, out_disc);
   } else if constexpr ((VAR & VAR_GUARD) != 0) {
-    mma_merge_kernel<KPL, CG, true, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
-                                                                         (u64*)out_packed, out_disc, no_push);
+    h->launches--;       // (counted below) the guarded kernel merges its own lists: no second launch
   } else if (h->push_ctx && out_packed && !out_scores && !out_rows && !out_disc) {
     // row-sharded search over peer memory: the winners go to every rank's gather buffer from this kernel
-    mma_merge_kernel<KPL, CG, false, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, nullptr, nullptr, nullptr,
+    mma_merge_kernel<KPL, CG, true><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, nullptr, nullptr, nullptr,
                                                                          nullptr, *h->push_ctx);
     h->push_fused = true;
   } else {
-    mma_merge_kernel<KPL, CG, false, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
+    mma_merge_kernel<KPL, CG, false><<<p.n_queries, 256, 0, st>>>(p, n_pairs, threshold, out_scores, (long long*)out_rows,
                                                                           (u64*)out_packed, out_disc, no_push);
   }
   MMF_LAUNCH_OK(h);
@@ -1580,6 +1625,8 @@ int mmf_mma_search(mmf_handle* h, const float* queries, int64_t n_queries, int t
   p.q_plane0 = reinterpret_cast<const uint4*>(planes);
   p.ovf = screen ? (int*)(sc + off_flag) : nullptr;
   p.progress = (u32*)(sc + off_prog);
+  p.grid_sync = p.progress + 255;                // (same cleared kilobyte: at most 148 progress words are in use)
+  p.g_scores = nullptr; p.g_rows = nullptr; p.g_packed = nullptr; p.g_disc = nullptr; p.g_threshold = 0.0;
   // window: a quarter of L2 per segment-and-then-some (a bf16 / fp16-hi tile is 128 KB); option "lockstep" = 0 turns it off
   p.lockstep_w = h->opt.lockstep ? 64 : 0;
   p.margin = screen ? 2.0f * SCREEN_EPS : 0.f;
