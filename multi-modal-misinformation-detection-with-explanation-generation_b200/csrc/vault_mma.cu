@@ -745,14 +745,20 @@ vault_mma_topk_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_con
           // a quarter writes half of the 256 columns)
           const uint4* src = p.q_plane0 + (long long)(qt * TILE_M + m) * (MMF_DIM * 2 / 16);
 #pragma unroll 1
-          for (int c = half * 4; c < half * 4 + 4; ++c) {
-            u32 w[32];
+          for (int c = half * 4; c < half * 4 + 4; c += 2) {      // 16 independent 128-bit loads in flight per thread
+            u32 w0[32], w1[32];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint4 x = __ldg(src + c * 8 + i);
-              w[4 * i] = x.x; w[4 * i + 1] = x.y; w[4 * i + 2] = x.z; w[4 * i + 3] = x.w;
+              w0[4 * i] = x.x; w0[4 * i + 1] = x.y; w0[4 * i + 2] = x.z; w0[4 * i + 3] = x.w;
             }
-            tmem_st32(lane_base + QA_COL + c * 32, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 x = __ldg(src + (c + 1) * 8 + i);
+              w1[4 * i] = x.x; w1[4 * i + 1] = x.y; w1[4 * i + 2] = x.z; w1[4 * i + 3] = x.w;
+            }
+            tmem_st32(lane_base + QA_COL + c * 32, w0);
+            tmem_st32(lane_base + QA_COL + (c + 1) * 32, w1);
           }
           tmem_wait_st();
           tcgen05_fence_before();
