@@ -335,6 +335,40 @@ def test_lockstep_producers_do_not_change_results(eng):
             assert np.array_equal(a, b, equal_nan=True), f"top-{k}: {what} differ with lock-step producers on / off"
 
 
+def test_topk_merge_sorted_lists_unsorted_lists_and_duplicates(eng):
+    """mmf_topk_merge: the fast path for lists sorted descending (what the search entries write: binary-search ranks), the
+    general path for anything else, and duplicate keys across lists -- all against a plain sort of the packed keys"""
+    if DOUBLE:
+        pytest.skip("kernel paths of the library")
+    n_rows, nq, k, world = 40000, 37, 100, 8
+    vault = synth.vault_rows(n_rows, seed=71)
+    q, _, _ = synth.queries(nq, n_rows, seed=72, vault_seed=71)
+    packed = []
+    for r in range(world):
+        lo, hi = r * n_rows // world, (r + 1) * n_rows // world
+        eng.vault_load(vault[lo:hi], mode="bf16", row_offset=lo)
+        packed.append(eng.vault_search_candidates(q, k).clone())
+    packed = torch.stack(packed)                                     # (world, nq, k) sorted lists
+    keys = packed.cpu().numpy().view(np.uint64)
+
+    def reference(kk, top):
+        flat = np.sort(kk.transpose(1, 0, 2).reshape(nq, -1), axis=1)[:, ::-1][:, :top]
+        return (flat & np.uint64(0xFFFFFFFF)).astype(np.int64)
+
+    for top in (100, 10):
+        rows_sorted = npy(eng.topk_merge(packed, top)[1])
+        assert np.array_equal(rows_sorted, reference(keys, top)), f"sorted lists, top-{top}"
+    g = torch.Generator().manual_seed(5)
+    perm = torch.stack([torch.stack([torch.randperm(k, generator=g) for _ in range(nq)]) for _ in range(world)]).to(packed.device)
+    shuffled = torch.gather(packed, 2, perm)                         # same keys, lists no longer sorted: general path
+    s_a, r_a, d_a = [npy(t) for t in eng.topk_merge(packed, 100)]
+    s_b, r_b, d_b = [npy(t) for t in eng.topk_merge(shuffled, 100)]
+    assert np.array_equal(r_a, r_b) and np.array_equal(s_a, s_b) and np.array_equal(d_a, d_b)
+    twice = torch.cat([packed[:2], packed[:2]])                      # every key twice, in different lists
+    r_dup = npy(eng.topk_merge(twice, 100)[1])
+    assert np.array_equal(r_dup, reference(twice.cpu().numpy().view(np.uint64), 100)), "duplicate keys across lists"
+
+
 def test_score_batch_entries_agree(eng):
     """Engine.score_batch (mmf_score_batch: one asynchronous call, device tensors) == Engine.score_batch_host (host buffers)
     == submit / collect with two batches in flight == cosine + search + verdict_assemble, with and without a modality mask"""
