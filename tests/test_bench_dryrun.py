@@ -166,3 +166,43 @@ def test_graft_entry_smoke_logic(monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     ge.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def test_clock_sampler_keeps_only_lines_inside_the_load_window(monkeypatch):
+    """ClockSampler.stop(): nvidia-smi lines stamped before window_start() or after stop() do not count; with no line in the
+    window the result says so instead of passing idle clocks off as clocks under load"""
+    import datetime
+    bench = _load_bench(monkeypatch)
+    t0 = datetime.datetime(2026, 1, 1, 12, 0, 0)
+
+    def stamp(ms):
+        return (t0 + datetime.timedelta(milliseconds=ms)).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+
+    lines = [f"{stamp(-300)}, 1965, 1965, 150.0, Not Active, Not Active, Not Active, Not Active",
+             f"{stamp(100)}, 1420, 1965, 600.0, Not Active, Not Active, Not Active, Active",
+             f"{stamp(200)}, 1400, 1965, 640.0, Not Active, Not Active, Not Active, Active",
+             f"{stamp(900)}, 1965, 1965, 200.0, Not Active, Not Active, Not Active, Not Active"]
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def communicate(self, timeout=None):
+            return "\n".join(lines) + "\n", ""
+
+    class _Now(datetime.datetime):
+        @classmethod
+        def now(cls, tz=None):
+            return t0 + datetime.timedelta(milliseconds=500)
+
+    s = bench.ClockSampler.__new__(bench.ClockSampler)
+    s.proc, s.t0, s.t1, s.wall0, s.held, s.spawned = _Proc(), t0, None, 0.0, True, 0.0
+    monkeypatch.setattr(bench.datetime, "datetime", _Now)
+    out = s.stop()
+    assert out["samples"] == 2 and out["sm_mhz"] == 1410.0 and out["sm_min_mhz"] == 1400.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"] and out["power_w_max"] == 640.0 and out["window"].startswith("timed region +")
+    s2 = bench.ClockSampler.__new__(bench.ClockSampler)
+    s2.proc, s2.t0, s2.t1, s2.wall0, s2.held, s2.spawned = _Proc(), t0 + datetime.timedelta(milliseconds=300), None, 0.0, False, 0.0
+    lines[:] = [lines[0], lines[3]]
+    out2 = s2.stop()
+    assert out2["samples"] == 2 and out2["window"].startswith("whole sampler lifetime")

@@ -417,3 +417,62 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     subprocess.run([gcc, "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", libdir, "-lmmf_b200", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().split("|")
     assert out[0].startswith("mmf_b200") and out[1:] == ["100", "0", "7813", "74", "2", "bad argument"]
+
+
+def test_sorted_list_merge_rule_matches_a_full_sort():
+    """Host model of topk_merge_kernel's fast path (csrc/vault_stream.cu): lists sorted descending, empty slots (key 0) last.
+    rank(list l, position j) = j + sum over the other lists of the number of keys that beat it, ties going to the lower
+    list index; only keys >= the smallest of the lists' ceil(top/L)-th entries need a rank.  The ranks below top are a
+    permutation of 0..top-1 and reproduce a full descending sort, with duplicates across lists and ragged lists."""
+    rng = np.random.default_rng(7)
+    for n_lists, k_in, top, fill in ((8, 100, 100, 100), (8, 100, 10, 100), (3, 16, 16, 9), (2, 5, 5, 5), (5, 40, 64, 33)):
+        lists = np.zeros((n_lists, k_in), np.uint64)
+        for l in range(n_lists):
+            n = fill if l % 2 == 0 else max(1, fill // 2)                  # ragged: some lists half empty
+            vals = rng.integers(1, 2000, size=n).astype(np.uint64)           # small range: duplicates within and across lists
+            lists[l, :n] = np.sort(vals)[::-1]
+        per = -(-top // n_lists)
+        floor_key = lists[:, per - 1].min() if per <= k_in else np.uint64(0)
+        win = np.zeros(top, np.uint64)
+        seen = set()
+        for l in range(n_lists):
+            for j in range(k_in):
+                key = lists[l, j]
+                if key == 0 or key < floor_key:
+                    continue
+                rank = j
+                for o in range(n_lists):
+                    if o != l:
+                        rank += int(np.sum(lists[o] > key)) + (int(np.sum(lists[o] == key)) if o < l else 0)
+                if rank < top:
+                    assert rank not in seen, "ranks must be unique"
+                    seen.add(rank)
+                    win[rank] = key
+        want = np.sort(lists.reshape(-1))[::-1][:top]
+        assert np.array_equal(win, want), (n_lists, k_in, top)
+        n_valid = int(np.count_nonzero(lists))
+        assert seen == set(range(min(top, n_valid)))
+
+
+def test_bucket_pool_minimum_is_a_lower_bound_whatever_was_published():
+    """bucket b holds the best score among the rows hashed to it that anybody PUBLISHED -- candidate
+    events or the seeds of a strip's warm-up (arbitrary subsets of the rows).  Once every bucket holds something, the
+    minimum over the buckets never exceeds the k-th best score of the whole shard (k distinct rows score at least that)."""
+    rng = np.random.default_rng(11)
+
+    def pool_bucket(row, k):                                              # csrc/vault_mma.cu: pool_bucket
+        return (((((row * 0x9E3779B1) & 0xFFFFFFFF) >> 16) * k) >> 16)
+
+    for k in (1, 5, 10, 16):
+        for trial in range(20):
+            n = int(rng.integers(k, 5000))
+            scores = rng.standard_normal(n).astype(np.float32)
+            kth = np.sort(scores)[::-1][k - 1]
+            pool = np.full(k, -np.inf, np.float32)
+            published = rng.random(n) < rng.uniform(0.01, 1.0)             # any subset: seeds, events, both
+            for row in np.nonzero(published)[0]:
+                b = pool_bucket(int(row), k)
+                assert 0 <= b < k
+                pool[b] = max(pool[b], scores[row])
+            if np.all(np.isfinite(pool)):
+                assert pool.min() <= kth
