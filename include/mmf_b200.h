@@ -118,7 +118,9 @@ int mmf_vault_search_candidates(mmf_handle* h, const float* queries, int64_t n_q
 
 /* packed: (n_lists, n_queries, k_in) uint64 candidates (e.g. the all-gathered shards).
  * Selects the global top_k per query under the same total order, so the result is
- * independent of the sharding.  Outputs as mmf_vault_search. */
+ * independent of the sharding.  Outputs as mmf_vault_search.  Any lists are accepted; lists
+ * sorted descending with their empty slots last (what every search entry of this library
+ * writes) take a faster path (binary-search ranks instead of a radix select). */
 int mmf_topk_merge(mmf_handle* h, const uint64_t* packed, int n_lists, int64_t n_queries, int k_in, int top_k,
                    double threshold, float* out_scores, int64_t* out_rows, float* out_discrepancy,
                    mmf_stream_t stream);
