@@ -22,11 +22,13 @@
 //       arithmetic) and selects the top-k among them.  A third of the MMA work and half of the DRAM bytes of the
 //       3-pass form; results bit-identical to the streaming kernel.  Bands that do not fit set a flag and the
 //       guarded 3-pass kernel (VAR_GUARD, launched after every screened search, returns at once otherwise) redoes
-//       the batch.
+//       the batch and merges its own lists behind a grid barrier: 4 launches per search (prep, screening, rerank,
+//       guarded no-op).
 //     top_k > 16: three passes,  q.v * 2^16 = qh.vh + qh.vl + ql.vh  (+ ql.vl, < 2^-22 relative, dropped)
 //       -> 8 TS + 4 SS UMMA per k-block, all into ONE fp32 TMEM accumulator; scores = D * 2^-16.
 //   * L2-aware schedule (pair_schedule): the pairs working on different query-tile groups sweep the
-//     same vault segment together, so a vault tile is fetched from DRAM by one and hit in L2 by the rest.
+//     same vault segment together, so a vault tile is fetched from DRAM by one and hit in L2 by the rest;
+//     their producers pace each other (lock-step, option "lockstep") so that they stay within an L2's worth.
 //
 // Roles (320 threads): warps 0-7 = epilogue (warp % 4 = the TMEM lane quarter it may touch), warp 8 =
 // TMA producer, warp 9 = TMEM owner + MMA issuer (the whole warp runs the loop in the uniform datapath,
@@ -39,23 +41,28 @@
 // Epilogue = streaming top-k.  TMEM lane == query, so each epilogue thread owns one query: it reads
 // 32 accumulator columns at a time (tcgen05.ld 32x32b.x32), compares their maximum with its private
 // threshold (a lower bound of its k-th best) and appends the rare survivors to its candidate list in
-// global memory (L2-resident).  Thresholds: exact for top_k <= 16 (the best values sorted in
-// registers), otherwise refreshed when a list is compacted (whole warp, topk.cuh); in both cases
-// tightened grid-wide: top_k <= 16 through a pool of bucket maxima (pool[row % buckets]: >= top_k distinct
-// rows, so the minimum over the buckets bounds the k-th best from below), top_k > 16 through a per-query
-// HISTOGRAM of candidate scores (VAR_HIST: the lower edge of the bin holding the k-th best counted candidate;
-// the bucket minimum sits near rank k*H(k), the histogram edge near rank 1.4*k).  A block works on "strips"
+// global memory (L2-resident).  The chunks of a tile are software-pipelined over two register buffers and the
+// accumulator is handed back as soon as its last column is in registers.  Thresholds are grid-wide lower bounds:
+// top_k <= 16 through a pool of exactly top_k hashed bucket maxima (pool_bucket: top_k distinct rows, so the minimum
+// over the buckets bounds the k-th best from below), SEEDED at the start of a strip with every thread's tile (or
+// chunk) maximum before anything is filtered; top_k > 16 through a per-query HISTOGRAM of candidate scores (the
+// lower edge of the bin holding the k-th best counted candidate; the bucket minimum sits near rank k*H(k), the
+// histogram edge near rank 1.4*k), refreshed every few tiles and when a list is compacted (whole warp, topk.cuh).
+// A candidate event is a group mask + one indexed jump + a single event body.  A block works on "strips"
 // (one group of query tiles x a run of vault tiles) so that state stays in registers; a tail kernel
 // (mma_merge_kernel / mma_rerank_kernel: parallel slot gather, one staging sweep, rank-by-counting or radix
 // select) produces the final top-k per query from the strips' lists.
 //
 // Switches: none are read from the environment on the search path.  mmf_set_option (include/mmf_b200.h) has "screen"
 // (0 = 3-pass kernel instead of the screened search, A/B + triage), "debug" (bit 0: skip the filter, 1: skip the vault
-// TMA, 2: skip the MMA warp's waits, 3: print in-kernel cycle counts), "force_cg" (1 or 2 CTAs per MMA) and
-// "flat_schedule" (plain flattened schedule instead of the L2-aware one).  Variants that lost their A/B on a B200 in
-// round 2 and were deleted: a 12-stage ring and an L2 prefetch for the screening pass (both slower: the loader is not
-// the limit, tools/tma_stream_micro.cu), the bucket-pool bound for top_k > 16 (histogram: 1.5x faster), the first
-// form of the merge / rerank tails.
+// TMA, 2: skip the MMA warp's waits, 3: print in-kernel cycle counts; the bits only exist in a -DMMF_MMA_TRIAGE=1
+// build), "force_cg" (1 or 2 CTAs per MMA), "flat_schedule" (plain flattened schedule instead of the L2-aware one),
+// "epi_parity" and "lockstep".  Variants that lost their A/B on a B200 in round 2 and were deleted: a 12-stage ring
+// and an L2 prefetch for the screening pass (both slower: the loader is not the limit, tools/tma_stream_micro.cu), the
+// bucket-pool bound for top_k > 16 (histogram: 1.5x faster), sorted per-thread registers for top_k <= 16, the
+// warm-up "storm" (one pair in eight filtering without a bound), a half-tile accumulator hand-off (N = 64 MMAs run
+// the tensor pipe at ~60 %), programmatic dependent launch between the kernels of a search (no gain), the first form
+// of the merge / rerank tails.
 #include "common.cuh"
 #include "topk.cuh"
 
